@@ -1,0 +1,169 @@
+"""The CPU oracle against every known answer the reference's own tests assert.
+
+CPU-only.  These pin oracle/lbfgs_oracle.cpp; the GPU parity tests then compare the CUDA path
+with the oracle.
+"""
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from util import rosenbrock_x0
+
+
+def test_p1_math_primitives(oracle):
+    """src/math.rs:84-122, exact."""
+    L = oracle.lib()
+    x = np.array([1.0, 1.0, 1.0])
+    y = np.array([1.0, 2.0, 3.0])
+    L.oracle_vecadd(y, x, 2.0, 3)
+    assert y.tolist() == [3.0, 4.0, 5.0]
+    assert L.oracle_vecdot(y, x, 3) == 12.0
+    L.oracle_vecscale(y, 2.0, 3)
+    assert y.tolist() == [6.0, 8.0, 10.0]
+    z = y.copy()
+    L.oracle_vecdiff(z, x, y, 3)
+    assert z.tolist() == [-5.0, -7.0, -9.0]
+    L.oracle_veccpy(y, x, 3)
+    assert y.tolist() == [1.0, 1.0, 1.0]
+    L.oracle_vecncpy(y, x, 3)
+    assert y.tolist() == [-1.0, -1.0, -1.0]
+    assert L.oracle_vec2norm(np.array([3.0, 4.0]), 2) == 5.0
+    assert L.oracle_vec2norminv(np.array([3.0, 4.0]), 2) == 0.2
+
+
+def test_p2_p3_rosenbrock_then_owlqn(oracle):
+    """tests/simple.rs:17-55."""
+    x = rosenbrock_x0(100)
+    r = oracle.minimize(oracle.default_param(), x, oracle.Objective.builtin("rosenbrock"))
+    assert r["status_name"] == "OK_CONVERGED"
+    assert abs(r["report"]["fx"]) <= 1e-4                      # tests/simple.rs:37
+    assert np.all(np.abs(r["x"] - 1.0) <= 1e-4)                # tests/simple.rs:38-40
+    # trajectory of the line-by-line restatement (provisional golden values)
+    assert len(r["trace"]) == 35 and r["report"]["neval"] == 40
+    assert r["report"]["fx"] == pytest.approx(2.186702802369137e-11, rel=1e-9)
+    assert r["x"][0] == pytest.approx(0.9999993398497918, rel=1e-12)
+    assert Counter(t["ncall"] for t in r["trace"]) == {0: 1, 1: 29, 2: 5}
+
+    p = oracle.default_param(orthantwise=1, owl_c=1.0, owl_start=0, owl_end=99)
+    r2 = oracle.minimize(p, r["x"].copy(), oracle.Objective.builtin("rosenbrock"))
+    assert r2["status_name"] == "OK_CONVERGED"
+    assert abs(r2["report"]["fx"] - 43.5025) <= 1e-4           # tests/simple.rs:52
+    assert abs(r2["x"][0] - 0.25) <= 1e-4                      # tests/simple.rs:53
+    assert abs(r2["x"][1] - 0.0575) <= 1e-4                    # tests/simple.rs:54
+    assert len(r2["trace"]) == 150 and r2["report"]["neval"] == 338
+
+
+def test_p4_booth(oracle):
+    """tests/simple.rs:57-83."""
+    r = oracle.minimize(oracle.default_param(), np.array([-1.2, 1.0]), oracle.Objective.builtin("booth"))
+    assert r["status_name"] == "OK_CONVERGED"
+    assert abs(r["x"][0] - 1.0) <= 1e-6 and abs(r["x"][1] - 3.0) <= 1e-6
+    assert len(r["trace"]) == 6 and r["report"]["neval"] == 6
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_p5_owlqn_poisson(oracle, golden_dir, mode):
+    """tests/owlqn.rs:5-63: fx = -42724.136705 +- 1e-6."""
+    d = np.load(os.path.join(golden_dir, "poisson_500x21.npz"))
+    p = oracle.default_param(orthantwise=1, owl_c=1.0, owl_start=1, owl_end=21, epsilon=1e-4,
+                             reduction_mode=mode)
+    r = oracle.minimize(p, np.zeros(21), oracle.Objective.glm("poisson", d["X"], d["y"], mode))
+    assert r["status_name"] == "OK_CONVERGED"
+    assert abs(r["report"]["fx"] - (-42724.136705)) <= 1e-6    # tests/owlqn.rs:60
+
+
+def test_p6_api_shape_max_iterations(oracle):
+    """src/lib.rs:38-50: with_max_iterations(5) returns Ok; quirk: 5 callbacks, 4 real iterations."""
+    r = oracle.minimize(oracle.default_param(max_iterations=5), rosenbrock_x0(100),
+                        oracle.Objective.builtin("rosenbrock"))
+    assert r["status_name"] == "OK_MAX_ITERATIONS"
+    assert [t["niter"] for t in r["trace"]] == [1, 2, 3, 4, 5]
+    assert r["trace"][0]["ncall"] == 0 and r["trace"][0]["neval"] == 1   # first propagate is a no-op
+
+
+def test_line_doc_example(oracle):
+    """src/line.rs:15-31: one MoreThuente search from the Rosenbrock start succeeds."""
+    r = oracle.minimize(oracle.default_param(max_iterations=2), rosenbrock_x0(100),
+                        oracle.Objective.builtin("rosenbrock"))
+    assert r["trace"][1]["ncall"] >= 1 and r["trace"][1]["fx"] < r["trace"][0]["fx"]
+
+
+def test_max_evaluations_and_cancel(oracle):
+    r = oracle.minimize(oracle.default_param(max_evaluations=10), rosenbrock_x0(100),
+                        oracle.Objective.builtin("rosenbrock"))
+    assert r["status_name"] == "OK_MAX_EVALUATIONS" and r["report"]["neval"] >= 10
+    r = oracle.minimize(oracle.default_param(), rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"),
+                        progress=lambda rec: rec["niter"] == 3)
+    assert r["status_name"] == "OK_CANCELLED" and len(r["trace"]) == 3
+
+
+def test_linesearch_disabled_quirk(oracle):
+    """max_linesearch 0/1 => 'x not changed'; 2 => one unconditional trial."""
+    for ml in (0, 1):
+        r = oracle.minimize(oracle.default_param(ls_max_linesearch=ml), rosenbrock_x0(100),
+                            oracle.Objective.builtin("rosenbrock"))
+        assert r["status_name"] == "ERR_X_NOT_CHANGED"
+    r = oracle.minimize(oracle.default_param(ls_max_linesearch=2, max_iterations=10), rosenbrock_x0(100),
+                        oracle.Objective.builtin("rosenbrock"))
+    assert all(t["ncall"] in (0, 1, 2) for t in r["trace"])
+    assert r["report"]["neval"] == 10   # one evaluation per real iteration + the initial one
+
+
+def test_evaluate_failure_paths(oracle):
+    """src/lbfgs.rs:454 (initial failure propagates); src/line.rs:213-220 + src/lbfgs.rs:645 (swallowed)."""
+    r = oracle.minimize(oracle.default_param(), rosenbrock_x0(10), oracle.Objective.python(lambda x, g: None))
+    assert r["status_name"] == "ERR_EVALUATE"
+    calls = {"n": 0}
+    L = oracle.lib()
+
+    def flaky(x, g):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            return None
+        import ctypes as C
+        return L.oracle_eval_rosenbrock(None, x.ctypes.data, g.ctypes.data, x.size, C.byref(C.c_int(0)))
+    r = oracle.minimize(oracle.default_param(), rosenbrock_x0(10), oracle.Objective.python(flaky))
+    assert r["status_name"] == "ERR_X_NOT_CHANGED"
+    assert r["report"]["last_ls_error"] == 1
+
+
+def test_all_linesearch_algorithms_converge(oracle):
+    for algo in (oracle.LS_MORETHUENTE, oracle.LS_ARMIJO, oracle.LS_WOLFE, oracle.LS_STRONG_WOLFE):
+        r = oracle.minimize(oracle.default_param(ls_algorithm=algo), rosenbrock_x0(100),
+                            oracle.Objective.builtin("rosenbrock"))
+        assert r["status_name"] == "OK_CONVERGED", algo
+        assert np.all(np.abs(r["x"] - 1.0) <= 1e-3)
+
+
+def test_damping_and_gradient_only_lj38(oracle, golden_dir):
+    """examples/lj.rs default call, and with_gradient_only (src/lbfgs.rs:283-289)."""
+    p0 = np.load(os.path.join(golden_dir, "lj38.npy")).ravel()
+    r = oracle.minimize(oracle.default_param(), p0.copy(), oracle.Objective.builtin("lj"))
+    assert r["status_name"] == "OK_CONVERGED" and r["report"]["fx"] < -160.0
+    p = oracle.default_param(ls_gradient_only=1, damping=1, ls_algorithm=oracle.LS_STRONG_WOLFE,
+                             ls_max_linesearch=2)
+    r = oracle.minimize(p, p0.copy(), oracle.Objective.builtin("lj"))
+    assert r["status_name"] == "OK_CONVERGED" and r["report"]["fx"] < -160.0
+    assert r["report"]["neval"] == r["report"]["niter"]
+    r = oracle.minimize(oracle.default_param(damping=1), p0.copy(), oracle.Objective.builtin("lj"))
+    assert r["status_name"] == "OK_CONVERGED"
+
+
+def test_owl_invalid_range_is_param_error(oracle):
+    """src/orthantwise.rs:64 assert!(start < end)."""
+    p = oracle.default_param(orthantwise=1, owl_start=5, owl_end=3)
+    r = oracle.minimize(p, rosenbrock_x0(10), oracle.Objective.builtin("rosenbrock"))
+    assert r["status_name"] == "ERR_INVALID_PARAM"
+
+
+def test_compensated_mode_matches_sequential_at_small_n(oracle):
+    a = oracle.minimize(oracle.default_param(), rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"),
+                        record_x=True)
+    b = oracle.minimize(oracle.default_param(reduction_mode=1), rosenbrock_x0(100),
+                        oracle.Objective.builtin("rosenbrock", 1), record_x=True)
+    assert len(a["trace"]) == len(b["trace"])
+    assert [t["ncall"] for t in a["trace"]] == [t["ncall"] for t in b["trace"]]
+    for ta, tb in zip(a["trace"], b["trace"]):
+        assert np.max(np.abs(ta["x"] - tb["x"]) / np.maximum(np.abs(ta["x"]), 1e-300)) < 1e-10
