@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement: L-BFGS iterations/s and HBM GB/s at n = 1e8, m = 6.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W  # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1]): Rosenbrock, x0 = (-1.2, 1.0) repeated (examples/sample.rs:10-17),
+n = 1e8 f64 per GPU, m = 6, MoreThuente, device-resident evaluate.  One "step" is one L-BFGS iteration
+(`propagate`, src/lbfgs.rs:503-560: line search with its evaluations, history update, two-loop).
+Multi-GPU is weak scaling: every rank owns a contiguous 1e8-element shard of an N*1e8 vector and the
+only exchange is the solver's scalar all-reduce.  `value` counts iterations/s normalised to n = 1e8
+(iterations/s * n_global / 1e8), i.e. plain iterations/s on one GPU.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_REF = 100_000_000
+METRIC = "lbfgs_iterations_per_sec_at_n1e8"
+UNIT = "it/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_survey(n, launches, kbytes):
+    """per iteration (6t + 6 + 8b) V solver-only + 2V t for the Rosenbrock evaluate,
+    V = 8n bytes: trial step 3V t + post-eval dots 3V t + history update 7V + two-loop (8b - 1) V.
+    t and b are the MEASURED evaluation / two-loop trip counts of the timed region."""
+    V = 8.0 * n
+    t = launches["evaluate"]
+    iters = launches["history"]
+    return 8.0 * t * V + 7.0 * iters * V + kbytes["backward"] + kbytes["forward"]
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(n_sample, warmup, steps, m=6, budget_s=None):
+    """Times the oracle (CPU port of the reference, single thread) on Rosenbrock n_sample: iterations
+    warmup+1 .. warmup+steps of the same workload.  Returns (it/s at n_sample, seconds, iterations timed)."""
+    import numpy as np
+    from oracle import oracle_lib as O
+    x = np.empty(n_sample)
+    x[0::2], x[1::2] = -1.2, 1.0
+    stamps = []
+
+    def on_progress(rec):
+        stamps.append(time.perf_counter())
+        if budget_s is not None and len(stamps) > warmup + 2 and stamps[-1] - stamps[warmup] > budget_s:
+            return True
+        return False
+    p = O.default_param(m=m, max_iterations=1 + warmup + steps)
+    O.minimize(p, x, O.Objective.builtin("rosenbrock"), progress=on_progress)
+    # stamps[i] is the end of propagate #i+1; propagate #1 is the no-op (src/lbfgs.rs:507-510)
+    done = len(stamps) - 1 - warmup
+    if done < 1:
+        return None, 0.0, 0
+    dt = stamps[-1] - stamps[warmup]
+    return done / dt, dt, done
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the path.  The reference is Rust and this
+    image has no rustc/cargo, so it is the oracle port (oracle/lbfgs_oracle.cpp), single-threaded like the
+    reference (README.md:24-25: rayon/SIMD are unchecked TODOs).  Each step is one L-BFGS iteration on a
+    bounded sample n_sample of the n = 1e8 workload; the rate is normalised to n = 1e8."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = int(args.ref_n)
+    rate, dt, done = cpu_oracle_rate(n_sample, args.warmup, args.steps, m=args.m)
+    value = rate * n_sample / N_REF
+    sample = (f"Rosenbrock n={n_sample} (same x0 pattern, m={args.m}, MoreThuente), iterations "
+              f"{args.warmup + 1}..{args.warmup + done}; it/s scaled by n_sample/1e8")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done * (N_REF / n_sample),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Rosenbrock n=1e8 f64 m=6 MoreThuente (BASELINE.json configs[1]), CPU oracle port",
+                   "n_sample": n_sample, "m": args.m},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import rust_lbfgs_b200 as R
+    from rust_lbfgs_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: rust_lbfgs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        comm = D.Comm(rank, world, local_rank)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    n_local = int(args.n)
+    n_global = n_local * world
+    goff = rank * n_local
+    K, W, m = args.steps, args.warmup, args.m
+
+    def make_builder():
+        b = R.lbfgs().with_m(m)
+        if comm is not None:
+            b = b.with_shard(comm, n_global, goff)
+        return b
+
+    def fill_x0(t):
+        t[0::2] = -1.2
+        t[1::2] = 1.0
+
+    obj = R.Rosenbrock()
+
+    # ---- device-resident run: `value`, roofline ------------------------------------------------
+    x = torch.empty(n_local, dtype=torch.float64, device=dev)
+    fill_x0(x)
+    state = make_builder().build(x, obj)
+    state.propagate()                       # propagate #1 is the reference's no-op (src/lbfgs.rs:507-510)
+    for _ in range(W):
+        state.propagate()
+    state.profile_enable(True)
+    state.profile_reset()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    ncalls = []
+    for _ in range(K):
+        p = state.propagate()
+        ncalls.append(p.ncall)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = D.max_over_ranks(ev0.elapsed_time(ev1))
+    prof = state.profile()
+    final = state.report()
+    state.finish()
+    state.close()
+
+    launches, kbytes, kms = prof["launches"], prof["bytes"], prof["ms"]
+    gpu_launches = int(sum(launches.values()))
+    it_per_s = K / (ms_total / 1e3)
+    value = it_per_s * n_global / N_REF
+
+    peak, peak_src = load_peaks()
+    dom = "backward" if launches["backward"] >= launches["forward"] else "forward"
+    dom_gbs = (kbytes[dom] / 1e9) / (kms[dom] / 1e3) if kms[dom] > 0 else None
+    traffic = load_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": f"two_loop_{dom}_step (k_{dom})", "achieved": dom_gbs, "peak": peak,
+        "unit": "GB/s", "frac": (dom_gbs / peak) if dom_gbs else None,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+        "peak_source": peak_src,
+        "launches": int(launches[dom]), "avg_launch_ms": kms[dom] / max(1, launches[dom]),
+        "algorithmic_bytes_per_launch": kbytes[dom] / max(1, launches[dom]),
+    }
+    kbytes["evaluate"] = 2.0 * 8.0 * n_local * launches["evaluate"]     # Rosenbrock: 1R 1W per evaluation
+    surv_bytes = algorithmic_bytes_survey(n_local, launches, kbytes)
+    iteration = {
+        "algorithmic_GBps_survey_formula": surv_bytes / 1e9 / (ms_total / 1e3),
+        "frac_of_peak_survey_formula": surv_bytes / 1e9 / (ms_total / 1e3) / peak,
+        "launched_GBps": sum(kbytes.values()) / 1e9 / (ms_total / 1e3),
+        "evaluations_per_iteration": launches["evaluate"] / max(1, K),
+        "kernel_ms": {k: round(v, 3) for k, v in kms.items() if v > 0},
+        "kernel_GBps": {k: round(kbytes[k] / 1e9 / (kms[k] / 1e3), 1) for k in kms if kms[k] > 0 and kbytes[k] > 0},
+        "host_syncs": prof["host_syncs"], "allreduces": prof["allreduces"],
+    }
+    del x
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the public API with HOST buffers: `e2e` ---------------------------------
+    # The reference-shaped call: x is a host slice (src/lbfgs.rs:399).  Timed: pinned host -> device copy
+    # of x0, a complete minimize() of W+K iterations (build + line searches + two-loops), device -> host
+    # copy of the result.  Copies happen once per solve, so bytes/step are 8n/(W+K) each way (+ the few
+    # scalars the solver reads back per iteration).
+    iters_e2e = W + K
+    xh = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    fill_x0(xh)
+    xd = torch.empty(n_local, dtype=torch.float64, device=dev)
+    builder = make_builder().with_max_iterations(iters_e2e + 1)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    xd.copy_(xh, non_blocking=True)
+    rep = builder.minimize(xd, obj, None)
+    xh.copy_(xd, non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    barrier()
+    e2e_s = D.max_over_ranks(t1 - t0)
+    e2e_iters = rep.niter - 1
+    e2e = {
+        "value": (e2e_iters / e2e_s) * n_global / N_REF, "unit": UNIT,
+        "h2d_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters),
+        "d2h_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters) + 64.0 * 3,
+        "iterations": e2e_iters, "seconds": e2e_s, "evaluations": rep.neval,
+        "note": "host x0 (pinned) -> HBM, full minimize() of W+K iterations incl. build, HBM -> host x",
+    }
+    del xd, xh
+
+    # ---- the reference's CPU path on this host (rank 0, N=1 only) -------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sample = int(args.cpu_n)
+        rate, dt, done = cpu_oracle_rate(n_sample, min(W, 2), args.cpu_steps, m=m, budget_s=25.0)
+        if rate:
+            cpu = {"value": rate * n_sample / N_REF, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"oracle (C++ port of the reference, 1 thread) Rosenbrock n={n_sample}, m={m}, "
+                             f"{done} iterations after {min(W, 2)} warm-up in {dt:.1f} s; it/s scaled by n_sample/1e8",
+                   "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Rosenbrock n=1e8 f64 per GPU, m=6, MoreThuente, device-resident evaluate "
+                                   "(BASELINE.json configs[1])",
+                       "n_per_gpu": n_local, "n_global": n_global, "m": m, "linesearch": "MoreThuente",
+                       "l2_policy": "inputs larger than L2 (19 vectors x 0.8 GB vs 126 MB)",
+                       "ncall_per_iteration": ncalls, "final_fx": final.fx, "final_gnorm": final.gnorm},
+            "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        comm.close()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=float, default=1e8, help="elements per GPU")
+    ap.add_argument("--m", type=int, default=6)
+    ap.add_argument("--ref-n", type=float, default=5e6, help="--impl reference: sample size")
+    ap.add_argument("--cpu-n", type=float, default=1e7, help="cpu_baseline sample size")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

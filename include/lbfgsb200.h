@@ -1,0 +1,290 @@
+/* lbfgsb200.h — C ABI of the B200-native L-BFGS / OWL-QN solver (liblbfgsb200.so).
+ *
+ * This is the drop-in boundary for the hot path of ybyygu/rust-lbfgs (`liblbfgs` 0.2.0).  The
+ * reference has no FFI of its own; its seams are `trait LbfgsMath<f64>` (src/math.rs:4-29), the
+ * builder `Lbfgs::with_*` / `minimize` / `build` / `propagate` (src/lbfgs.rs:185-566) and the two
+ * user closures `E: FnMut(&[f64], &mut [f64]) -> Result<f64>` (src/core.rs:10-13) and
+ * `G: FnMut(&Progress) -> bool` (src/lbfgs.rs:402).  Each entry point below names the reference
+ * item it replaces.  A Rust `-sys` crate (rust_lbfgs_b200/rust/), the C++ builder
+ * (rust_lbfgs_b200/cxx/lbfgsb200.hpp) and the Python ctypes mirror (rust_lbfgs_b200/api.py) all
+ * bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs with 8-byte fields only; no CUDA or torch types.  A
+ *     `stream` argument is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - every vector (x, g, d, xp, gp, pg, the m-deep s/y ring) lives in HBM for the whole solve;
+ *     `x_dev` is caller-owned device memory, 16-byte aligned, length n_local; everything else is
+ *     owned by the solver handle.
+ *   - all arithmetic is IEEE f64; element-wise results are bit-identical to the reference's
+ *     (kernels are built with -fmad=false), reductions are deterministic two-level tree sums.
+ *   - one handle per GPU / rank; a handle is not thread-safe (same as the reference).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     LBFGSB200_ERR_CUDA.
+ */
+#ifndef LBFGSB200_H
+#define LBFGSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBFGSB200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    LBFGSB200_OK_CONVERGED = 0,             /* gnorm / max(1, xnorm) <= epsilon   src/lbfgs.rs:714-722 */
+    LBFGSB200_OK_MAX_ITERATIONS = 1,        /* src/lbfgs.rs:726-735 */
+    LBFGSB200_OK_MAX_EVALUATIONS = 2,       /* src/lbfgs.rs:739-748 */
+    LBFGSB200_OK_CANCELLED = 3,             /* progress callback returned non-zero  src/lbfgs.rs:412-416 */
+    LBFGSB200_OK = 0,
+    LBFGSB200_ERR_EVALUATE = -1,            /* Err from evaluate at the initial point  src/lbfgs.rs:454 */
+    LBFGSB200_ERR_X_NOT_CHANGED = -2,       /* "x not changed with step ..."  src/lbfgs.rs:645-646 */
+    LBFGSB200_ERR_G_NOT_CHANGED = -3,       /* "gx not changed"  src/lbfgs.rs:655 */
+    LBFGSB200_ERR_LINESEARCH = -4,          /* Err out of LineSearch::find itself  src/line.rs:198-201,208 */
+    LBFGSB200_ERR_INVALID_PARAM = -5,       /* the reference's assert!/panic on parameters */
+    LBFGSB200_ERR_OWLQN_ZERO_DIRECTION = -6,/* assert_ne!(d.vec2norm(), 0.0)  src/orthantwise.rs:160 */
+    LBFGSB200_ERR_INVALID_DNORM = -7,       /* ensure!(dnorm.is_sign_positive())  src/lbfgs.rs:544 */
+    LBFGSB200_ERR_CUDA = -20,               /* CUDA runtime failure, or no CUDA device */
+    LBFGSB200_ERR_NCCL = -21,               /* NCCL failure, or libnccl.so.2 not loadable */
+    LBFGSB200_ERR_STATE = -22               /* call order violated (e.g. propagate before build) */
+};
+
+/* line-search algorithms  src/line.rs:39-80 */
+enum {
+    LBFGSB200_LS_MORETHUENTE = 0,
+    LBFGSB200_LS_BACKTRACKING_ARMIJO = 1,
+    LBFGSB200_LS_BACKTRACKING_WOLFE = 2,
+    LBFGSB200_LS_BACKTRACKING_STRONG_WOLFE = 3
+};
+
+/* swallowed line-search errors (src/line.rs:213-220 prints and reverts), report.last_ls_error */
+enum {
+    LBFGSB200_LS_ERR_NONE = 0,
+    LBFGSB200_LS_ERR_EVALUATE = 1,
+    LBFGSB200_LS_ERR_ROUNDING = 2,          /* src/line.rs:292-298 */
+    LBFGSB200_LS_ERR_XTOL = 3,              /* src/line.rs:300-302 */
+    LBFGSB200_LS_ERR_MAX_STEP = 4,          /* src/line.rs:305-308,171-174 */
+    LBFGSB200_LS_ERR_MIN_STEP = 5,          /* src/line.rs:310-313,167-170 */
+    LBFGSB200_LS_ERR_OUT_OF_INTERVAL = 6,   /* src/line.rs:474-476 */
+    LBFGSB200_LS_ERR_INCREASE_GRADIENT = 7, /* src/line.rs:477-479 */
+    LBFGSB200_LS_ERR_INCORRECT_TMINMAX = 8  /* src/line.rs:480-483 */
+};
+
+/* ---- parameters --------------------------------------------------------------------------- */
+/* LbfgsParam (src/lbfgs.rs:72-154) + LineSearch (src/line.rs:91-148) + Orthantwise
+ * (src/orthantwise.rs:19-45), flattened.  `struct_size` must be sizeof(lbfgsb200_param_t). */
+typedef struct lbfgsb200_param {
+    int64_t struct_size;
+    int64_t m;                      /* history depth; default 6 (no setter in the reference: src/lbfgs.rs:163,182) */
+    double  epsilon;                /* 1e-5 */
+    int64_t past;                   /* 0; stored, never consumed (dead code src/lbfgs.rs:766-787) */
+    double  delta;                  /* 1e-5; stored, never consumed */
+    int64_t max_iterations;         /* 0 = unlimited */
+    int64_t max_evaluations;        /* 0 = unlimited */
+    int64_t ls_algorithm;           /* LBFGSB200_LS_* */
+    double  ls_ftol;                /* 1e-4 */
+    double  ls_gtol;                /* 0.9 */
+    double  ls_xtol;                /* f64::EPSILON */
+    double  ls_min_step;            /* 1e-20 */
+    double  ls_max_step;            /* 1e+20 */
+    int64_t ls_max_linesearch;      /* 20 */
+    int64_t ls_gradient_only;       /* 0 */
+    int64_t orthantwise;            /* 0 = None */
+    double  owl_c;                  /* 1.0 */
+    int64_t owl_start;              /* 0   (global index) */
+    int64_t owl_end;                /* < 0 = None => n_global */
+    double  initial_inverse_hessian;/* 1.0 */
+    double  max_step_size;          /* 1.0 */
+    int64_t damping;                /* 0 */
+    int64_t constrain_step_size;    /* 1 (no setter in the reference: src/lbfgs.rs:153,174) */
+} lbfgsb200_param_t;
+
+/* Lbfgs::default()  src/lbfgs.rs:156-177, src/line.rs:150-163, src/orthantwise.rs:47-55 */
+void lbfgsb200_param_default(lbfgsb200_param_t *param);
+
+/* ---- callbacks ---------------------------------------------------------------------------- */
+/* Device-resident evaluate: replaces `E: FnMut(&[f64], &mut [f64]) -> Result<f64>`
+ * (src/core.rs:10-13,120).  Must enqueue, on `stream`, work that writes the gradient of this
+ * rank's shard to g_dev[0..n_local) and this rank's PARTIAL objective value to *fx_dev (device
+ * memory; the solver sums the partials over ranks).  Must not synchronise.  Non-zero = Err. */
+typedef int (*lbfgsb200_eval_fn)(void *user, const double *x_dev, double *g_dev, int64_t n_local,
+                                 void *stream, double *fx_dev);
+
+/* Progress  src/core.rs:221-250; x/gx are device pointers to this rank's shard */
+typedef struct lbfgsb200_progress {
+    const double *x_dev;
+    const double *gx_dev;
+    int64_t n_local;
+    int64_t n_global;
+    double  fx;
+    double  xnorm;
+    double  gnorm;
+    double  step;
+    int64_t niter;
+    int64_t neval;
+    int64_t ncall;
+} lbfgsb200_progress_t;
+
+/* replaces `G: FnMut(&Progress) -> bool`; non-zero cancels  src/lbfgs.rs:402,412-416 */
+typedef int (*lbfgsb200_progress_fn)(void *user, const lbfgsb200_progress_t *progress);
+
+/* Report  src/core.rs:271-285 (+ diagnostics) */
+typedef struct lbfgsb200_report {
+    double  fx;
+    double  xnorm;
+    double  gnorm;
+    int64_t neval;
+    int64_t niter;                  /* number of propagate() calls made */
+    int64_t last_ls_error;          /* LBFGSB200_LS_ERR_* of the last swallowed line-search failure */
+    int64_t status;                 /* status of the last minimize() */
+} lbfgsb200_report_t;
+
+/* ---- multi-GPU communicator (one NCCL rank per process/GPU) ------------------------------- */
+typedef struct lbfgsb200_comm lbfgsb200_comm_t;
+#define LBFGSB200_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id and ships it to the other ranks (torch.distributed / MPI / a file) */
+int  lbfgsb200_comm_unique_id(char id[LBFGSB200_UNIQUE_ID_BYTES]);
+int  lbfgsb200_comm_create(const char id[LBFGSB200_UNIQUE_ID_BYTES], int rank, int nranks, int device,
+                           lbfgsb200_comm_t **out);
+void lbfgsb200_comm_destroy(lbfgsb200_comm_t *comm);
+/* in-place sum of `count` doubles in device memory over all ranks (ncclAllReduce, ncclDouble, ncclSum) */
+int  lbfgsb200_comm_allreduce_sum(lbfgsb200_comm_t *comm, double *buf_dev, int count, void *stream);
+
+/* ---- solver lifecycle --------------------------------------------------------------------- */
+typedef struct lbfgsb200_solver lbfgsb200_solver_t;
+
+/* Problem::new (src/core.rs:59-75) + the ring allocation of build (src/lbfgs.rs:449): allocates
+ * g/gp/x'/d (+pg, wp for OWL-QN) and the 2m history vectors in HBM.
+ *   n_local        this rank's shard length;  n_global  total length (== n_local on one GPU)
+ *   global_offset  global index of local element 0 (even, so Rosenbrock pairs stay together)
+ *   comm           NULL on one GPU */
+int  lbfgsb200_create(const lbfgsb200_param_t *param, int64_t n_local, int64_t n_global,
+                      int64_t global_offset, int device, void *stream, lbfgsb200_comm_t *comm,
+                      lbfgsb200_solver_t **out);
+void lbfgsb200_destroy(lbfgsb200_solver_t *solver);
+const char *lbfgsb200_last_error(const lbfgsb200_solver_t *solver);
+
+/* Lbfgs::minimize  src/lbfgs.rs:399-421.  Returns an LBFGSB200_OK_* / ERR_* status; x_dev holds
+ * the final point on return. */
+int lbfgsb200_minimize(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user,
+                       lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report);
+
+/* The iterative API  src/lbfgs.rs:443-566 */
+int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user);
+/* is_converged (src/lbfgs.rs:489-494): 1 = stop, 0 = continue; *stop_status gets the OK_* reason */
+int lbfgsb200_is_converged(lbfgsb200_solver_t *solver, int *stop_status);
+int lbfgsb200_propagate(lbfgsb200_solver_t *solver, lbfgsb200_progress_t *progress_out);
+int lbfgsb200_report(lbfgsb200_solver_t *solver, lbfgsb200_report_t *report_out);
+/* copies the current point into the caller's x_dev if it lives in the solver's own buffer
+ * (x and xp ping-pong instead of save_state's copies, src/core.rs:207-210) */
+int lbfgsb200_finish(lbfgsb200_solver_t *solver);
+/* device pointers of the current point / gradient / search direction (this rank's shard) */
+const double *lbfgsb200_x(const lbfgsb200_solver_t *solver);
+const double *lbfgsb200_gx(const lbfgsb200_solver_t *solver);
+const double *lbfgsb200_direction(const lbfgsb200_solver_t *solver);
+
+/* Reference-shaped convenience: x is a HOST slice as in `minimize(&mut x, ..)` (src/lbfgs.rs:399).
+ * Copies x to the device, solves on one GPU, copies the result back (both copies inside the call). */
+int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int64_t n, int device,
+                            lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
+                            void *progress_user, lbfgsb200_report_t *report);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+enum {
+    LBFGSB200_K_DOTS = 0,       /* {g.d, g.g, x.x} in one read                       src/core.rs:114-116,183-194 */
+    LBFGSB200_K_OWL_PG = 1,     /* l1 norm + pseudo-gradient + norms                 src/orthantwise.rs:70-112 */
+    LBFGSB200_K_INIT_DIR = 2,   /* d = -g | -pg, d.d, g.d                            src/core.rs:95-101 */
+    LBFGSB200_K_TRIAL = 3,      /* x = xp + step*d (+ orthant projection)            src/core.rs:155-164 */
+    LBFGSB200_K_ORTHANT = 4,    /* wp                                                src/core.rs:167-180 */
+    LBFGSB200_K_HISTORY = 5,    /* s, y, s.s, y.s, y.y, s.d, s.Bs                    src/lbfgs.rs:640-656 */
+    LBFGSB200_K_DAMP = 6,       /* Powell damping of y                               src/lbfgs.rs:666-689 */
+    LBFGSB200_K_BACKWARD = 7,   /* two-loop backward step                            src/lbfgs.rs:582-591 */
+    LBFGSB200_K_FORWARD = 8,    /* two-loop forward step                             src/lbfgs.rs:594-601 */
+    LBFGSB200_K_EVALUATE = 9,   /* the user's device evaluate */
+    LBFGSB200_K_PRIMITIVE = 10, /* unfused LbfgsMath primitives                      src/math.rs:31-82 */
+    LBFGSB200_K_COUNT = 11
+};
+typedef struct lbfgsb200_profile {
+    int64_t launches[LBFGSB200_K_COUNT];        /* kernels launched (evaluate: callback invocations) */
+    double  bytes[LBFGSB200_K_COUNT];           /* algorithmic bytes moved (passes * 8 * n_local) */
+    double  ms[LBFGSB200_K_COUNT];              /* CUDA-event time on the solver's stream (timing on) */
+    int64_t host_syncs;                         /* stream synchronisations made by the solver */
+    int64_t allreduces;                         /* scalar all-reduces issued */
+} lbfgsb200_profile_t;
+/* timing != 0 brackets every launch with CUDA events on the solver's stream */
+int lbfgsb200_profile_enable(lbfgsb200_solver_t *solver, int timing);
+int lbfgsb200_profile_get(lbfgsb200_solver_t *solver, lbfgsb200_profile_t *out);
+int lbfgsb200_profile_reset(lbfgsb200_solver_t *solver);
+
+/* ---- LbfgsMath primitives on device pointers  src/math.rs:31-82 ---------------------------- */
+int lbfgsb200_vecadd(double *y_dev, const double *x_dev, double c, int64_t n, void *stream);     /* y += c*x */
+int lbfgsb200_vecdot(const double *x_dev, const double *y_dev, int64_t n, void *stream, double *out_host);
+int lbfgsb200_vecscale(double *y_dev, double c, int64_t n, void *stream);                        /* y *= c */
+int lbfgsb200_veccpy(double *y_dev, const double *x_dev, int64_t n, void *stream);               /* y = x */
+int lbfgsb200_vecncpy(double *y_dev, const double *x_dev, int64_t n, void *stream);              /* y = -x */
+int lbfgsb200_vecdiff(double *z_dev, const double *x_dev, const double *y_dev, int64_t n, void *stream); /* z = x - y */
+int lbfgsb200_vec2norm(const double *x_dev, int64_t n, void *stream, double *out_host);
+int lbfgsb200_vec2norminv(const double *x_dev, int64_t n, void *stream, double *out_host);
+
+/* ---- fused hot-path steps, exposed for unit parity ----------------------------------------- */
+/* {g.d, g.g, x.x}; d_dev may be NULL (then out[0] = 0) */
+int lbfgsb200_dots3(const double *g_dev, const double *d_dev, const double *x_dev, int64_t n, void *stream,
+                    double out_host[3]);
+/* x = xp + step*d; wp_dev (int8 signs) non-NULL applies the orthant projection on [start,end) */
+int lbfgsb200_trial_step(double *x_dev, const double *xp_dev, const double *d_dev, double step, int64_t n,
+                         const signed char *wp_dev, int64_t start, int64_t end, void *stream);
+/* OWL-QN pseudo-gradient (src/orthantwise.rs:70-112): out = {sum c|x| on [start,end), pg.pg, x.x} */
+int lbfgsb200_owl_pseudo_gradient(double *pg_dev, const double *x_dev, const double *g_dev, int64_t n,
+                                  double c, int64_t start, int64_t end, void *stream, double out_host[3]);
+/* wp = xp == 0 ? signum(-pg) : signum(xp)  (src/core.rs:167-180), stored as int8 */
+int lbfgsb200_owl_orthant(signed char *wp_dev, const double *xp_dev, const double *pg_dev, int64_t n,
+                          void *stream);
+/* d = 0 where signum(d) != signum(-pg) on [start,end) (src/orthantwise.rs:140-161); out = {d.d after} */
+int lbfgsb200_owl_constrain_direction(double *d_dev, const double *pg_dev, int64_t n, int64_t start,
+                                      int64_t end, void *stream, double out_host[1]);
+
+/* ---- built-in device objectives (lbfgsb200_eval_fn-compatible) ------------------------------ */
+typedef struct lbfgsb200_objective lbfgsb200_objective_t;
+/* default_evaluate (Rosenbrock)  src/lib.rs:79-94; n_local must be even */
+int  lbfgsb200_objective_rosenbrock(int device, lbfgsb200_objective_t **out);
+/* Booth function  tests/simple.rs:65-74 (n = 2) */
+int  lbfgsb200_objective_booth(int device, lbfgsb200_objective_t **out);
+/* dense GLM, X row-major nrow x ncol in device memory (not copied), y nrow:
+ *   kind 0 = Poisson log-linear  tests/owlqn.rs:22-43;  kind 1 = logistic (BASELINE.json configs[2]) */
+int  lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const double *y_dev, int64_t nrow,
+                             int64_t ncol, lbfgsb200_objective_t **out);
+/* all-pairs Lennard-Jones  examples/lj.rs:20-64,114-117; n = 3 * atoms */
+int  lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, lbfgsb200_objective_t **out);
+void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective);
+/* the lbfgsb200_eval_fn for every built-in objective: pass the objective handle as `user` */
+int  lbfgsb200_objective_eval(void *objective, const double *x_dev, double *g_dev, int64_t n_local,
+                              void *stream, double *fx_dev);
+
+/* ---- line-search state machines (pure host code; exposed so the scalar logic can be checked
+ *      without a GPU)  src/line.rs:226-399, 446-709, 716-784 ----------------------------------- */
+typedef struct lbfgsb200_linesearch lbfgsb200_linesearch_t;
+lbfgsb200_linesearch_t *lbfgsb200_linesearch_begin(const lbfgsb200_param_t *param, int orthantwise,
+                                                   double finit, double dginit, double step);
+/* returns 1 and *step_out = next trial step; 0 when finished (see _result) */
+int  lbfgsb200_linesearch_next(lbfgsb200_linesearch_t *ls, double *step_out);
+void lbfgsb200_linesearch_feed(lbfgsb200_linesearch_t *ls, int eval_ok, double f, double dg);
+/* after _next returned 0: *ncall, final *step; returns LBFGSB200_LS_ERR_* (0 = success) */
+int  lbfgsb200_linesearch_result(lbfgsb200_linesearch_t *ls, int64_t *ncall, double *step);
+void lbfgsb200_linesearch_end(lbfgsb200_linesearch_t *ls);
+
+/* ---- device-memory helpers for hosts without a CUDA binding (Rust, ctypes) ----------------- */
+int  lbfgsb200_device_count(void);
+int  lbfgsb200_device_alloc(int device, int64_t bytes, void **out_dev);
+int  lbfgsb200_device_free(void *dev);
+int  lbfgsb200_copy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+int  lbfgsb200_copy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
+int  lbfgsb200_stream_synchronize(void *stream);
+int  lbfgsb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBFGSB200_H */

@@ -725,6 +725,38 @@ int oracle_minimize(const oracle_param_t *param, double *x, int64_t n, oracle_ev
     return status;
 }
 
+// The public low-level entry of src/line.rs:15-31: Problem::new, evaluate, a caller-chosen search
+// direction, LineSearch::find.  Returns 0 or ORACLE_ERR_*; *ls_error gets the swallowed
+// line-search error (0 = the search itself succeeded), *ncall / *step the results of find.
+int oracle_line_search(const oracle_param_t *param, double *x, int64_t n, const double *d, double *step,
+                       oracle_eval_fn eval, void *eval_user, int64_t *ncall, int64_t *ls_error, double *fx_out) {
+    g_mode = (int)param->reduction_mode;
+    Owl owl;
+    owl.on = param->orthantwise != 0;
+    owl.c = param->owl_c;
+    owl.start = param->owl_start;
+    owl.end = param->owl_end;
+    LineSearch ls;
+    ls.algorithm = (int)param->ls_algorithm;
+    ls.ftol = param->ls_ftol;
+    ls.gtol = param->ls_gtol;
+    ls.xtol = param->ls_xtol;
+    ls.min_step = param->ls_min_step;
+    ls.max_step = param->ls_max_step;
+    ls.max_linesearch = param->ls_max_linesearch;
+    ls.gradient_only = param->ls_gradient_only != 0;
+    Problem prb(x, n, eval, eval_user, owl);
+    if (!prb.evaluate()) return ORACLE_ERR_EVALUATE;
+    veccpy(prb.d.data(), d, n);
+    prb.save_state();
+    int64_t swallowed = 0, count = 0;
+    if (!linesearch_find(ls, prb, *step, count, swallowed)) return ORACLE_ERR_LINESEARCH;
+    *ncall = count;
+    *ls_error = swallowed;
+    *fx_out = prb.fx;
+    return 0;
+}
+
 void   oracle_vecadd(double *y, const double *x, double c, int64_t n) { vecadd(y, x, c, n); }
 double oracle_vecdot(const double *x, const double *y, int64_t n) { g_mode = 0; return vecdot(x, y, n); }
 void   oracle_vecscale(double *y, double c, int64_t n) { vecscale(y, c, n); }

@@ -107,6 +107,10 @@ int oracle_minimize(const oracle_param_t *param, double *x, int64_t n,
                     oracle_progress_fn progress, void *progress_user,
                     oracle_report_t *report, char *errbuf, size_t errbuf_len);
 
+/* src/line.rs:15-31: one LineSearch::find from x along a caller-chosen direction d */
+int oracle_line_search(const oracle_param_t *param, double *x, int64_t n, const double *d, double *step,
+                       oracle_eval_fn eval, void *eval_user, int64_t *ncall, int64_t *ls_error, double *fx_out);
+
 /* LbfgsMath for [f64], src/math.rs:31-82 */
 void   oracle_vecadd(double *y, const double *x, double c, int64_t n);
 double oracle_vecdot(const double *x, const double *y, int64_t n);

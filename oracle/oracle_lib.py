@@ -96,6 +96,10 @@ def lib():
         L.oracle_owl_pseudo_gradient.argtypes = [dp, dp, dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
         L.oracle_owl_project.argtypes = [dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int]
         L.oracle_owl_orthant.argtypes = [dp, dp, dp, C.c_int64]
+        L.oracle_line_search.restype = C.c_int
+        L.oracle_line_search.argtypes = [C.POINTER(Param), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double),
+                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_double)]
         for name in ("rosenbrock", "booth", "poisson", "logistic", "lj"):
             f = getattr(L, "oracle_eval_" + name)
             f.restype = C.c_double
@@ -185,3 +189,17 @@ def minimize(param, x, objective, record_x=False, progress=None):
                 report=dict(fx=rep.fx, xnorm=rep.xnorm, gnorm=rep.gnorm, neval=rep.neval, niter=rep.niter,
                             last_ls_error=rep.last_ls_error),
                 error=err.value.decode())
+
+
+def line_search(param, x, d, step, objective):
+    """One LineSearch::find (src/line.rs:193-223) from numpy x along d.  x is updated in place.
+
+    Returns dict(rc, ncall, ls_error, step, fx, x)."""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    stp = C.c_double(step)
+    ncall, lserr, fx = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+    rc = L.oracle_line_search(C.byref(param), x.ctypes.data, x.size, d.ctypes.data, C.byref(stp), objective.fn_ptr,
+                              objective.user, C.byref(ncall), C.byref(lserr), C.byref(fx))
+    return dict(rc=rc, ncall=ncall.value, ls_error=lserr.value, step=stp.value, fx=fx.value, x=x)

@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's public API over the C ABI.
+
+    from rust_lbfgs_b200 import lbfgs, Rosenbrock
+    report = (lbfgs().with_max_iterations(5)
+                     .minimize(x, Rosenbrock(), lambda prgr: False))
+
+mirrors `lbfgs().with_max_iterations(5).minimize(&mut x, evaluate, progress)` (src/lib.rs:9-53,
+src/lbfgs.rs:185-421): same builder names, argument meaning, defaults and error behaviour
+(`assert!` -> ValueError, `Err` -> LbfgsError).  The difference is the one north_star asks for:
+`x` is a float64 CUDA tensor (or any object with data_ptr()/numel()) that stays in HBM, and
+`evaluate` is a device-resident objective — a built-in one (objectives.py) or a Python callable
+`evaluate(x, gx) -> fx` working on CUDA tensor views.  All compute happens in liblbfgsb200.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+from . import _lib
+from ._lib import EVAL_FN, PROGRESS_FN, STATUS_NAMES
+
+
+class LbfgsError(RuntimeError):
+    """The `Err(..)` arm of the reference's `Result<Report>`."""
+
+    def __init__(self, status, message, report=None):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+        self.status_name = STATUS_NAMES.get(status, str(status))
+        self.message = message
+        self.report = report
+
+
+@dataclass
+class Progress:
+    """src/core.rs:221-250; x / gx are device views (this rank's shard)."""
+    x: object
+    gx: object
+    fx: float
+    xnorm: float
+    gnorm: float
+    step: float
+    niter: int
+    neval: int
+    ncall: int
+
+
+@dataclass
+class Report:
+    """src/core.rs:271-285 (+ status and diagnostics)."""
+    fx: float
+    xnorm: float
+    gnorm: float
+    neval: int
+    niter: int = 0
+    last_ls_error: int = 0
+    status: int = 0
+
+    @property
+    def status_name(self):
+        return STATUS_NAMES.get(self.status, str(self.status))
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ holder so torch can alias solver-owned HBM."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_view(ptr, n, device):
+    import torch
+    return torch.as_tensor(_CudaView(ptr, n), device=torch.device("cuda", device))
+
+
+def _ptr_n_device(x):
+    if hasattr(x, "data_ptr"):
+        if hasattr(x, "dtype") and str(x.dtype) != "torch.float64":
+            raise ValueError("x must be float64")
+        if hasattr(x, "is_contiguous") and not x.is_contiguous():
+            raise ValueError("x must be contiguous")
+        if hasattr(x, "is_cuda") and not x.is_cuda:
+            raise ValueError("x must live in device memory (CUDA); rust_lbfgs_b200 has no CPU path")
+        dev = x.device.index if getattr(x, "device", None) is not None and x.device.index is not None else 0
+        return int(x.data_ptr()), int(x.numel()), int(dev)
+    raise TypeError("x must expose data_ptr()/numel() (a CUDA float64 tensor or a DeviceBuffer)")
+
+
+def _current_stream(device):
+    try:
+        import torch
+        return int(torch.cuda.current_stream(device).cuda_stream)
+    except Exception:
+        return 0
+
+
+class _Evaluate:
+    """Adapts a built-in objective or a Python callable to lbfgsb200_eval_fn."""
+
+    def __init__(self, evaluate, device):
+        self.keep = []
+        if hasattr(evaluate, "_eval_ptr"):
+            self.fn = evaluate._eval_ptr()
+            self.user = evaluate._user_ptr(device)
+            self.keep.append(evaluate)
+        elif callable(evaluate):
+            import torch
+
+            def tramp(_user, x_dev, g_dev, n, stream, fx_dev):
+                try:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=device)) if stream else _null():
+                        xv = device_view(x_dev, n, device)
+                        gv = device_view(g_dev, n, device)
+                        fx = evaluate(xv, gv)
+                        if fx is None:
+                            return 1
+                        fv = device_view(fx_dev, 1, device)
+                        if isinstance(fx, torch.Tensor):
+                            fv.copy_(fx.reshape(1).to(torch.float64))
+                        else:
+                            fv.fill_(float(fx))
+                    return 0
+                except Exception:  # an Err from evaluate
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = EVAL_FN(tramp)
+            self.fn = C.cast(cb, C.c_void_p)
+            self.user = None
+            self.keep += [cb, evaluate]
+        else:
+            raise TypeError("evaluate must be a built-in objective or a callable evaluate(x, gx) -> fx")
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class Lbfgs:
+    """The builder, src/lbfgs.rs:179-384.  `lbfgs()` returns `Lbfgs()` (src/lib.rs:74-76)."""
+
+    def __init__(self):
+        self.param = _lib.default_param()
+        self._comm = None
+        self._shard = None  # (n_global, global_offset)
+
+    # -- src/lbfgs.rs:194-383, in source order ------------------------------------------------
+    def with_epsilon(self, epsilon):
+        _require(_sign_positive(epsilon), "Invalid parameter epsilon specified.")
+        self.param.epsilon = epsilon
+        return self
+
+    def with_initial_step_size(self, b):
+        _require(_sign_positive(b), "Invalid beta parameter for scaling the initial step size.")
+        self.param.initial_inverse_hessian = b
+        return self
+
+    def with_max_step_size(self, s):
+        _require(_sign_positive(s), "Invalid max_step_size parameter.")
+        self.param.max_step_size = s
+        return self
+
+    def with_damping(self, damped):
+        self.param.damping = 1 if damped else 0
+        return self
+
+    def with_orthantwise(self, c, start, end=None):
+        _require(_sign_positive(c), "Invalid parameter orthantwise c parameter specified.")
+        self.param.orthantwise = 1
+        self.param.owl_c = c
+        self.param.owl_start = int(start)
+        self.param.owl_end = -1 if end is None else int(end)
+        return self
+
+    def with_linesearch_ftol(self, ftol):
+        _require(ftol >= 0.0, "Invalid parameter ftol specified.")
+        self.param.ls_ftol = ftol
+        return self
+
+    def with_linesearch_gtol(self, gtol):
+        _require(0.0 <= gtol < 1.0 and gtol > self.param.ls_ftol, "Invalid parameter gtol specified.")
+        self.param.ls_gtol = gtol
+        return self
+
+    def with_gradient_only(self):
+        self.param.ls_gradient_only = 1
+        self.param.damping = 1
+        self.param.ls_algorithm = _lib.LS_BACKTRACKING_STRONG_WOLFE
+        return self
+
+    def with_max_linesearch(self, n):
+        self.param.ls_max_linesearch = int(n)
+        return self
+
+    def with_linesearch_xtol(self, xtol):
+        _require(xtol >= 0.0, "Invalid parameter xtol specified.")
+        self.param.ls_xtol = xtol
+        return self
+
+    def with_linesearch_min_step(self, min_step):
+        _require(min_step >= 0.0, "Invalid parameter min_step specified.")
+        self.param.ls_min_step = min_step
+        return self
+
+    def with_max_iterations(self, niter):
+        self.param.max_iterations = int(niter)
+        return self
+
+    def with_max_evaluations(self, neval):
+        self.param.max_evaluations = int(neval)
+        return self
+
+    def with_fx_delta(self, delta, past):
+        _require(delta >= 0.0, "Invalid parameter delta specified.")
+        self.param.past = int(past)
+        self.param.delta = delta
+        return self
+
+    def with_linesearch_algorithm(self, algo):
+        table = {"MoreThuente": _lib.LS_MORETHUENTE, "BacktrackingArmijo": _lib.LS_BACKTRACKING_ARMIJO,
+                 "BacktrackingStrongWolfe": _lib.LS_BACKTRACKING_STRONG_WOLFE,
+                 "BacktrackingWolfe": _lib.LS_BACKTRACKING_WOLFE, "Backtracking": _lib.LS_BACKTRACKING_WOLFE}
+        if algo not in table:
+            raise NotImplementedError(algo)  # unimplemented!(), src/lbfgs.rs:379
+        self.param.ls_algorithm = table[algo]
+        return self
+
+    # -- extensions (not in the reference) -------------------------------------------------------
+    def with_m(self, m):
+        """History depth.  The reference has no setter (LbfgsParam.m = 6, src/lbfgs.rs:163,182);
+        BASELINE.json configs[4] needs m = 20."""
+        _require(int(m) >= 1, "Invalid parameter m specified.")
+        self.param.m = int(m)
+        return self
+
+    def with_shard(self, comm, n_global, global_offset):
+        """This rank's x is elements [global_offset, global_offset + len(x)) of an n_global vector;
+        `comm` is a rust_lbfgs_b200.dist.Comm (one NCCL rank per GPU)."""
+        self._comm = comm
+        self._shard = (int(n_global), int(global_offset))
+        return self
+
+    # -- src/lbfgs.rs:399-421, 443-481 -------------------------------------------------------------
+    def build(self, x, evaluate):
+        return LbfgsState(self, x, evaluate)
+
+    def minimize(self, x, evaluate, progress=None):
+        L = _lib.lib()
+        ptr, n, device = _ptr_n_device(x)
+        solver = _make_solver(self, n, device)
+        try:
+            ev = _Evaluate(evaluate, device)
+            cb = None
+            cbp = None
+            if progress is not None:
+                def on_progress(_user, pp):
+                    return 1 if progress(_progress_from_c(pp.contents, device)) else 0
+                cb = PROGRESS_FN(on_progress)
+                cbp = C.cast(cb, C.c_void_p)
+            rep = _lib.Report()
+            st = L.lbfgsb200_minimize(solver, ptr, ev.fn, ev.user, cbp, None, C.byref(rep))
+            report = _report_from_c(rep)
+            report.status = st
+            if st < 0:
+                raise LbfgsError(st, L.lbfgsb200_last_error(solver).decode(), report)
+            return report
+        finally:
+            L.lbfgsb200_destroy(solver)
+
+
+def lbfgs():
+    """Create a default LBFGS optimizer (src/lib.rs:74-76)."""
+    return Lbfgs()
+
+
+class LbfgsState:
+    """L-BFGS optimization state allowing iterative propagation (src/lbfgs.rs:425-566)."""
+
+    def __init__(self, builder, x, evaluate):
+        self._L = _lib.lib()
+        ptr, n, device = _ptr_n_device(x)
+        self._device = device
+        self._x_owner = x
+        self._solver = _make_solver(builder, n, device)
+        self._ev = _Evaluate(evaluate, device)
+        st = self._L.lbfgsb200_build(self._solver, ptr, self._ev.fn, self._ev.user)
+        if st != 0:
+            msg = self._L.lbfgsb200_last_error(self._solver).decode()
+            self.close()
+            raise LbfgsError(st, msg)
+
+    def is_converged(self):
+        st = C.c_int(0)
+        r = self._L.lbfgsb200_is_converged(self._solver, C.byref(st))
+        self.stop_status = st.value if r == 1 else None
+        return r == 1
+
+    def propagate(self):
+        p = _lib.Progress()
+        st = self._L.lbfgsb200_propagate(self._solver, C.byref(p))
+        if st != 0:
+            raise LbfgsError(st, self._L.lbfgsb200_last_error(self._solver).decode())
+        return _progress_from_c(p, self._device)
+
+    def report(self):
+        rep = _lib.Report()
+        self._L.lbfgsb200_report(self._solver, C.byref(rep))
+        return _report_from_c(rep)
+
+    def finish(self):
+        """Make the caller's x hold the current point (x/xp ping-pong between two buffers)."""
+        st = self._L.lbfgsb200_finish(self._solver)
+        if st != 0:
+            raise LbfgsError(st, self._L.lbfgsb200_last_error(self._solver).decode())
+
+    # instrumentation
+    def profile_enable(self, timing=True):
+        self._L.lbfgsb200_profile_enable(self._solver, 1 if timing else 0)
+
+    def profile_reset(self):
+        self._L.lbfgsb200_profile_reset(self._solver)
+
+    def profile(self):
+        p = _lib.Profile()
+        self._L.lbfgsb200_profile_get(self._solver, C.byref(p))
+        return {
+            "launches": {k: p.launches[i] for i, k in enumerate(_lib.K_NAMES)},
+            "bytes": {k: p.bytes[i] for i, k in enumerate(_lib.K_NAMES)},
+            "ms": {k: p.ms[i] for i, k in enumerate(_lib.K_NAMES)},
+            "host_syncs": p.host_syncs, "allreduces": p.allreduces,
+        }
+
+    def close(self):
+        if getattr(self, "_solver", None):
+            self._L.lbfgsb200_destroy(self._solver)
+            self._solver = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- helpers --------------------------------------------------------------------------------------
+def _require(cond, msg):
+    if not cond:
+        raise ValueError(msg)  # the reference's assert!(.., msg) panics
+
+
+def _sign_positive(v):
+    import math
+    return math.copysign(1.0, float(v)) > 0.0  # f64::is_sign_positive
+
+
+def _make_solver(builder, n, device):
+    L = _lib.lib()
+    n_global, goff = (n, 0) if builder._shard is None else builder._shard
+    comm = builder._comm._handle if builder._comm is not None else None
+    out = C.c_void_p()
+    st = L.lbfgsb200_create(C.byref(builder.param), n, n_global, goff, device, _current_stream(device), comm,
+                            C.byref(out))
+    if st == -5:
+        raise ValueError("invalid L-BFGS parameter (the reference would panic)")
+    if st != 0:
+        raise LbfgsError(st, "lbfgsb200_create failed (no CUDA device? rust_lbfgs_b200 has no CPU fallback)")
+    return out
+
+
+def _progress_from_c(p, device):
+    return Progress(x=device_view(p.x_dev, p.n_local, device), gx=device_view(p.gx_dev, p.n_local, device),
+                    fx=p.fx, xnorm=p.xnorm, gnorm=p.gnorm, step=p.step, niter=p.niter, neval=p.neval, ncall=p.ncall)
+
+
+def _report_from_c(r):
+    return Report(fx=r.fx, xnorm=r.xnorm, gnorm=r.gnorm, neval=r.neval, niter=r.niter,
+                  last_ls_error=r.last_ls_error, status=r.status)

@@ -1,0 +1,63 @@
+// kernels.h — host-side launchers of the sm_100a hot-path kernels (kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "types.h"
+
+namespace lb {
+
+// Everything a launch needs besides its operands.
+struct Launch {
+    cudaStream_t stream = nullptr;
+    int max_grid = 148 * 8;   // CTAs: a multiple of the SM count (set from the device at create)
+    bool streaming = true;    // evict-first loads/stores (vectors much larger than L2)
+    ReduceWs ws{};            // level-2 reduction workspace
+    int64_t *launch_counter = nullptr;
+};
+
+// K2  {g.d, g.g, x.x} in one read; d may be null.           src/core.rs:114-116,183-194
+void launch_dots(const Launch &L, const double *g, const double *d, const double *x, int64_t n, double *out);
+// K3  l1 = sum c|x| on [start,end), pseudo-gradient, pg.pg, x.x (, g.d when d != null)
+//                                                            src/orthantwise.rs:70-112
+void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g, const double *d, int64_t n,
+                   double c, int64_t start, int64_t end, int64_t goff, double *out);
+// K0  d = -src; out = {d.d, src.d}                           src/core.rs:95-101, src/lbfgs.rs:457-461
+void launch_init_dir(const Launch &L, double *d, const double *src, int64_t n, double *out);
+// K1  x = xp + step*d; wp != null: x = 0 where signum(x) != wp on [start,end)
+//                                                            src/core.rs:155-164, src/orthantwise.rs:118-133
+void launch_trial(const Launch &L, double *x, const double *xp, const double *d, double step, int64_t n,
+                  const signed char *wp, int64_t start, int64_t end, int64_t goff);
+// K4  wp = xp == 0 ? signum(-pg) : signum(xp)                src/core.rs:167-180
+void launch_orthant(const Launch &L, signed char *wp, const double *xp, const double *pg, int64_t n);
+// K5  s = x - xp; y = g - gp; out = {s.s, y.s, y.y, s.(-g), s.(gp*nstep)}
+//                                                            src/lbfgs.rs:640-656,670-673, first trip of :587
+//     (pg != null: OWL-QN, the first alpha uses d = -pg)
+void launch_history(const Launch &L, const double *x, const double *xp, const double *g, const double *gp,
+                    const double *pg, double *s, double *y, int64_t n, double nstep, bool damping, double *out);
+// K6  y = ((gp*nstep)*omt) + theta*y                         src/lbfgs.rs:675-680
+void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, double omt, double theta);
+// K7  alpha = *red_in / ys_j; q = (first ? -g : q) - alpha*y_j; !last: out = {s_next.q}
+//     last: d = q*gamma, out = {y_j.d}                        src/lbfgs.rs:582-591,597
+void launch_backward(const Launch &L, bool first, bool last, double *q, const double *g, const double *y,
+                     const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
+                     double *alpha_out, double *out);
+// K8  beta = *red_in / ys_j; r += (alpha_j - beta) s_j; !last: out = {y_next.r}
+//     last: out = {r.r, g.r}; last+owl: out = {r.r (before projection), pg.d, d.d (after)}
+//                                                            src/lbfgs.rs:594-601,543, src/orthantwise.rs:140-161
+void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
+                    const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
+                    int64_t start, int64_t end, int64_t goff, double *out);
+// OWL-QN direction projection alone (K8's epilogue as a stand-alone op): out = {d.d after}
+void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t n, int64_t start, int64_t end,
+                          int64_t goff, double *out);
+
+// K11  LbfgsMath primitives                                   src/math.rs:31-82
+void launch_vecadd(const Launch &L, double *y, const double *x, double c, int64_t n);
+void launch_vecscale(const Launch &L, double *y, double c, int64_t n);
+void launch_veccpy(const Launch &L, double *y, const double *x, int64_t n, bool negate);
+void launch_vecdiff(const Launch &L, double *z, const double *x, const double *y, int64_t n);
+void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n, double *out);
+
+}  // namespace lb

@@ -1,0 +1,297 @@
+// objectives.cu — device-resident objectives with the lbfgsb200_eval_fn signature.
+//
+// They exist so a solve (and the benchmark) never moves x or g over PCIe: each one reads x from
+// HBM, writes g to HBM and leaves this rank's partial f in *fx_dev, all on the caller's stream.
+//   Rosenbrock     default_evaluate, src/lib.rs:79-94            (streaming, 1R 1W)
+//   Booth          tests/simple.rs:65-74                          (n = 2)
+//   GLM            tests/owlqn.rs:22-43 (Poisson) + logistic       (dense X in HBM)
+//   Lennard-Jones  examples/lj.rs:20-64,114-117                    (all pairs, FP64)
+// Element-wise arithmetic keeps the reference's operation order (-fmad=false).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <new>
+
+#include "../../include/lbfgsb200.h"
+#include "reduce.cuh"
+#include "solver.h"
+
+namespace lb {
+namespace {
+
+enum Kind { OBJ_ROSENBROCK = 0, OBJ_BOOTH = 1, OBJ_GLM = 2, OBJ_LJ = 3 };
+
+struct Objective {
+    int kind = 0;
+    DeviceInfo dev{};
+    ReduceWs ws{};
+    // GLM
+    int glm_kind = 0;
+    const double *X = nullptr, *y = nullptr;
+    int64_t nrow = 0, ncol = 0;
+    double *t = nullptr;         // per-row residual
+    double *gpart = nullptr;     // [row_chunks][ncol] partial gradients
+    int row_chunks = 0;
+    // LJ
+    double eps = 1.0, sigma = 1.0;
+};
+
+// ---- Rosenbrock ------------------------------------------------------------------------------
+template <bool S>
+struct RosenOp {
+    const double *x;
+    double *g;
+    struct Regs { double2 x; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const { r.x = ld2<S>(x, i); }
+    __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[1]) const {
+        const double x0 = r.x.x, x1 = r.x.y;
+        const double t1 = 1.0 - x0;                         // lib.rs:85
+        const double t2 = 10.0 * (x1 - x0 * x0);            // :86
+        double2 o;
+        o.y = 20.0 * t2;                                    // :87
+        o.x = -2.0 * (x0 * o.y + t1);                       // :88
+        acc[0] += t1 * t1 + t2 * t2;                        // :89
+        st2<S>(g, i, o);
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[1]) const {}
+};
+template <bool S>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock(RosenOp<S> op, int64_t n, ReduceWs ws, double *fx) {
+    double acc[1] = {0.0};
+    stream_pairs<1, 4>(n, op, acc);
+    grid_reduce<1>(acc, ws, fx);
+}
+
+// ---- Booth -----------------------------------------------------------------------------------
+__global__ void k_booth(const double *x, double *g, double *fx) {
+    const double x1 = x[0], x2 = x[1];
+    const double a = x1 + 2.0 * x2 - 7.0;
+    const double b = 2.0 * x1 + x2 - 5.0;
+    *fx = a * a + b * b;                                    // powi(2), tests/simple.rs:68
+    g[0] = 10.0 * x1 + 8.0 * x2 - 34.0;                     // :69
+    g[1] = 8.0 * x1 + 10.0 * x2 - 38.0;                     // :70
+}
+
+// ---- GLM, pass 1: z = X w per row (one warp per row), f terms, residual t ---------------------
+// kind 0 Poisson:  f += -(y z - exp z) ... accumulated as (y z - exp z) and negated once, t = y - exp z
+// kind 1 logistic: f += softplus(z) - y z,                                                t = sigmoid(z) - y
+__global__ void __launch_bounds__(kThreads) k_glm_rows(const double *__restrict__ X, const double *__restrict__ y,
+                                                       const double *__restrict__ w, double *__restrict__ t,
+                                                       int64_t nrow, int64_t ncol, int kind, ReduceWs ws, double *fx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    double acc[1] = {0.0};
+    for (int64_t r = warp0; r < nrow; r += nwarps) {
+        const double *row = X + r * ncol;
+        double z = 0.0;
+        for (int64_t c = lane; c < ncol; c += 32) z += w[c] * row[c];
+        z = warp_sum(z);
+        z = __shfl_sync(0xffffffffu, z, 0);
+        if (lane == 0) {
+            const double yr = y[r];
+            if (kind == 0) {
+                const double e = exp(z);
+                acc[0] += yr * z - e;
+                t[r] = yr - e;
+            } else {
+                const double sp = fmax(z, 0.0) + log1p(exp(-fabs(z)));
+                double mu;
+                if (z >= 0.0) mu = 1.0 / (1.0 + exp(-z));
+                else { const double e = exp(z); mu = e / (1.0 + e); }
+                acc[0] += sp - yr * z;
+                t[r] = mu - yr;
+            }
+        }
+    }
+    if (kind == 0) acc[0] = -1.0 * acc[0];
+    grid_reduce<1>(acc, ws, fx);
+}
+
+// ---- GLM, pass 2: partial gradients over row chunks (thread = column; coalesced rows) ---------
+__global__ void __launch_bounds__(kThreads) k_glm_grad_partial(const double *__restrict__ X, const double *__restrict__ t,
+                                                               double *__restrict__ gpart, int64_t nrow, int64_t ncol,
+                                                               int rows_per_chunk, int kind) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    int64_t r1 = r0 + rows_per_chunk;
+    if (r1 > nrow) r1 = nrow;
+    if (c >= ncol) return;
+    double a = 0.0;
+    if (kind == 0) for (int64_t r = r0; r < r1; ++r) a += t[r] * (-X[r * ncol + c]);   // (-X^T) t, owlqn.rs:40
+    else for (int64_t r = r0; r < r1; ++r) a += t[r] * X[r * ncol + c];
+    gpart[(int64_t)blockIdx.y * ncol + c] = a;
+}
+__global__ void __launch_bounds__(kThreads) k_glm_grad_final(const double *__restrict__ gpart, double *__restrict__ g,
+                                                             int64_t ncol, int chunks) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= ncol) return;
+    double a = 0.0;
+    for (int k = 0; k < chunks; ++k) a += gpart[(int64_t)k * ncol + c];
+    g[c] = a;
+}
+
+// ---- Lennard-Jones: thread = atom, partners streamed through shared memory in index order -----
+// For atom i the reference adds its pair forces in ascending partner order (pairs (i, j<i) during
+// row i, then pairs (i', i) for i' > i), and (p_i - p_j) == -(p_j - p_i) exactly, so a sequential
+// ascending loop over all partners reproduces forces[i] bit for bit.
+constexpr int kLjTile = 256;
+__global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
+                                                double eps, double sigma, ReduceWs ws, double *fx) {
+    __shared__ double sp[kLjTile * 3];
+    const int64_t i = (int64_t)blockIdx.x * kLjTile + threadIdx.x;
+    const bool active = i < natoms;
+    double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
+    if (active) { pi0 = x[3 * i]; pi1 = x[3 * i + 1]; pi2 = x[3 * i + 2]; }
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
+    for (int64_t base = 0; base < natoms; base += kLjTile) {
+        const int64_t cnt = (natoms - base < kLjTile) ? (natoms - base) : kLjTile;
+        __syncthreads();
+        for (int64_t q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * base + q];
+        __syncthreads();
+        if (!active) continue;
+        for (int jj = 0; jj < (int)cnt; ++jj) {
+            const int64_t j = base + jj;
+            if (j == i) continue;
+            const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
+            const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);       // vecdist, lj.rs:50
+            const double qq = sigma / r;
+            const double q2 = qq * qq;
+            const double s6 = q2 * (q2 * q2);                         // powi(sigma/r, 6), lj.rs:23,30
+            if (j < i) e += 4.0 * eps * (s6 * s6 - s6);               // pair_energy, counted once, lj.rs:51
+            const double gr = 24.0 * eps * (s6 - 2.0 * (s6 * s6)) / r;  // pair_gradient, lj.rs:32
+            // forces[i][k] += g*dr/r with dr = p_j - p_i = -d  (lj.rs:55-57)
+            f0 += gr * (-d0) / r;
+            f1 += gr * (-d1) / r;
+            f2 += gr * (-d2) / r;
+        }
+    }
+    if (active) {  // gx = -forces, lj.rs:116
+        g[3 * i] = -f0;
+        g[3 * i + 1] = -f1;
+        g[3 * i + 2] = -f2;
+    }
+    double acc[1] = {e};
+    grid_reduce<1>(acc, ws, fx);
+}
+
+int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t stream, double *fx) {
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    switch (o->kind) {
+        case OBJ_ROSENBROCK: {
+            if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;  // the reference indexes x[i+1] (lib.rs:86)
+            const int64_t tile = (int64_t)kThreads * 4;
+            int64_t tiles = ((n >> 1) + tile - 1) / tile;
+            const int64_t cap = (int64_t)o->dev.sm_count * o->dev.blocks_per_sm;
+            if (tiles > cap) tiles = cap;
+            if (tiles < 1) tiles = 1;
+            const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
+            if (streaming) k_rosenbrock<true><<<(int)tiles, kThreads, 0, stream>>>({x, g}, n, o->ws, fx);
+            else k_rosenbrock<false><<<(int)tiles, kThreads, 0, stream>>>({x, g}, n, o->ws, fx);
+            break;
+        }
+        case OBJ_BOOTH:
+            if (n != 2) return LBFGSB200_ERR_INVALID_PARAM;
+            k_booth<<<1, 1, 0, stream>>>(x, g, fx);
+            break;
+        case OBJ_GLM: {
+            if (n != o->ncol) return LBFGSB200_ERR_INVALID_PARAM;
+            int64_t blocks = (o->nrow + kWarps - 1) / kWarps;
+            const int64_t cap = (int64_t)o->dev.sm_count * 8;
+            if (blocks > cap) blocks = cap;
+            k_glm_rows<<<(int)blocks, kThreads, 0, stream>>>(o->X, o->y, x, o->t, o->nrow, o->ncol, o->glm_kind, o->ws, fx);
+            const int rows_per_chunk = (int)((o->nrow + o->row_chunks - 1) / o->row_chunks);
+            dim3 grid((unsigned)((o->ncol + kThreads - 1) / kThreads), (unsigned)o->row_chunks);
+            k_glm_grad_partial<<<grid, kThreads, 0, stream>>>(o->X, o->t, o->gpart, o->nrow, o->ncol, rows_per_chunk, o->glm_kind);
+            k_glm_grad_final<<<grid.x, kThreads, 0, stream>>>(o->gpart, g, o->ncol, o->row_chunks);
+            break;
+        }
+        case OBJ_LJ: {
+            if (n % 3 != 0 || n < 3) return LBFGSB200_ERR_INVALID_PARAM;
+            const int64_t na = n / 3;
+            const int64_t blocks = (na + kLjTile - 1) / kLjTile;
+            if (blocks > o->ws.stride) return LBFGSB200_ERR_INVALID_PARAM;
+            k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, na, o->eps, o->sigma, o->ws, fx);
+            break;
+        }
+        default:
+            return LBFGSB200_ERR_INVALID_PARAM;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
+int make(int device, int kind, Objective **out) {
+    if (!out) return LBFGSB200_ERR_INVALID_PARAM;
+    *out = nullptr;
+    Objective *o = new (std::nothrow) Objective();
+    if (!o) return LBFGSB200_ERR_CUDA;
+    o->kind = kind;
+    int rc = query_device(device, &o->dev);
+    if (rc != 0) { delete o; return rc; }
+    if (cudaSetDevice(device) != cudaSuccess) { delete o; return LBFGSB200_ERR_CUDA; }
+    rc = alloc_reduce_ws(o->dev, &o->ws);
+    if (rc != 0) { delete o; return rc; }
+    *out = o;
+    return 0;
+}
+
+}  // namespace
+}  // namespace lb
+
+extern "C" {
+
+int lbfgsb200_objective_rosenbrock(int device, lbfgsb200_objective_t **out) {
+    return lb::make(device, lb::OBJ_ROSENBROCK, reinterpret_cast<lb::Objective **>(out));
+}
+int lbfgsb200_objective_booth(int device, lbfgsb200_objective_t **out) {
+    return lb::make(device, lb::OBJ_BOOTH, reinterpret_cast<lb::Objective **>(out));
+}
+int lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const double *y_dev, int64_t nrow, int64_t ncol,
+                            lbfgsb200_objective_t **out) {
+    if (!X_dev || !y_dev || nrow < 1 || ncol < 1 || kind < 0 || kind > 1) return LBFGSB200_ERR_INVALID_PARAM;
+    lb::Objective *o = nullptr;
+    int rc = lb::make(device, lb::OBJ_GLM, &o);
+    if (rc != 0) return rc;
+    o->glm_kind = kind;
+    o->X = X_dev;
+    o->y = y_dev;
+    o->nrow = nrow;
+    o->ncol = ncol;
+    int chunks = (int)((nrow + 255) / 256);
+    const int col_blocks = (int)((ncol + lb::kThreads - 1) / lb::kThreads);
+    const int want = (o->dev.sm_count * 8 + col_blocks - 1) / col_blocks;
+    if (chunks > want) chunks = want;
+    if (chunks < 1) chunks = 1;
+    o->row_chunks = chunks;
+    if (cudaMalloc((void **)&o->t, sizeof(double) * (size_t)nrow) != cudaSuccess ||
+        cudaMalloc((void **)&o->gpart, sizeof(double) * (size_t)chunks * (size_t)ncol) != cudaSuccess) {
+        lbfgsb200_objective_destroy(reinterpret_cast<lbfgsb200_objective_t *>(o));
+        return LBFGSB200_ERR_CUDA;
+    }
+    *out = reinterpret_cast<lbfgsb200_objective_t *>(o);
+    return 0;
+}
+int lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, lbfgsb200_objective_t **out) {
+    lb::Objective *o = nullptr;
+    int rc = lb::make(device, lb::OBJ_LJ, &o);
+    if (rc != 0) return rc;
+    o->eps = epsilon;
+    o->sigma = sigma;
+    *out = reinterpret_cast<lbfgsb200_objective_t *>(o);
+    return 0;
+}
+void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
+    lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
+    if (!o) return;
+    if (o->t) cudaFree(o->t);
+    if (o->gpart) cudaFree(o->gpart);
+    lb::free_reduce_ws(&o->ws);
+    delete o;
+}
+int lbfgsb200_objective_eval(void *objective, const double *x_dev, double *g_dev, int64_t n_local, void *stream,
+                             double *fx_dev) {
+    if (!objective || !x_dev || !g_dev || !fx_dev) return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::eval_impl(reinterpret_cast<lb::Objective *>(objective), x_dev, g_dev, n_local, (cudaStream_t)stream, fx_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// reduce.cuh — streaming map + deterministic two-level reduction skeleton (sm_100a, f64).
+//
+// Every hot-path kernel is "stream a few n-vectors once, write at most a couple, and emit up to
+// kMaxAcc dot-product-like sums".  Level 1: each thread keeps its accumulators over a fixed set of
+// elements, a fixed-shape warp-shuffle tree and a fixed-shape cross-warp tree give one partial per
+// CTA.  Level 2: the LAST CTA to finish (atomic ticket) sums the per-CTA partials in index order
+// with the same fixed trees and writes the results to device memory.  Which CTA runs level 2 does
+// not matter: the summation order depends only on (n, grid), so results are bit-reproducible run
+// to run.  This replaces the sequential fold of `vecdot` (src/math.rs:40-42) — and fuses what the
+// survey calls K9 (`finalize_reduce`) into the producing kernel, so no extra launch is needed.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "types.h"
+
+namespace lb {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Sum acc[] over the CTA; result valid in thread 0.
+template <int NACC>
+__device__ __forceinline__ void block_sum(double (&acc)[NACC], double (*sm)[kWarps]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = warp_sum(acc[a]);
+        if (lane == 0) sm[a][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            double v = (lane < kWarps) ? sm[a][lane] : 0.0;
+#pragma unroll
+            for (int off = kWarps / 2; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            acc[a] = v;
+        }
+    }
+}
+
+// Level 1 + level 2.  `out[a]` receives the grid-wide sum of accumulator a.
+template <int NACC>
+__device__ __forceinline__ void grid_reduce(double (&acc)[NACC], const ReduceWs &ws, double *__restrict__ out) {
+    __shared__ double sm[NACC][kWarps];
+    __shared__ bool is_last;
+    block_sum<NACC>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) __stcg(&ws.partials[(size_t)a * ws.stride + blockIdx.x], acc[a]);
+        __threadfence();
+        unsigned int t = atomicAdd(ws.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads)
+            v += __ldcg(&ws.partials[(size_t)a * ws.stride + i]);
+        acc[a] = v;
+    }
+    __syncthreads();  // sm reuse
+    block_sum<NACC>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) out[a] = acc[a];
+        *ws.ticket = 0u;
+    }
+}
+
+// 128-bit streaming loads/stores.  kStream selects evict-first (.cs) accesses for vectors that are
+// far larger than L2 (n = 1e8: 0.8 GB per vector vs 126 MB of L2); small problems keep default
+// caching so the working set stays L2-resident between kernels.
+template <bool kStream>
+__device__ __forceinline__ double2 ld2(const double *__restrict__ p, int64_t i) {
+    const double2 *q = reinterpret_cast<const double2 *>(p) + i;
+    if (kStream) return __ldcs(q);
+    return *q;
+}
+template <bool kStream>
+__device__ __forceinline__ void st2(double *__restrict__ p, int64_t i, double2 v) {
+    double2 *q = reinterpret_cast<double2 *>(p) + i;
+    if (kStream) __stcs(q, v); else *q = v;
+}
+
+// Streams n elements through `op` as double2 pairs: U independent 128-bit loads per input vector
+// are issued per thread before any use (memory-level parallelism), tiles are contiguous per CTA
+// (coalesced 4 KB * U per vector), grid-stride over tiles.  An odd trailing element is handled by
+// one thread through op.tail().
+//   Op::Regs                      registers holding one pair per input vector
+//   op.load(Regs&, int64 pair)    issue the loads
+//   op.apply(Regs&, int64 pair, double (&acc)[NACC])   compute, store, accumulate
+//   op.tail(int64 elem, acc)      scalar path for element n-1 when n is odd
+template <int NACC, int U, class Op>
+__device__ __forceinline__ void stream_pairs(int64_t n, Op &op, double (&acc)[NACC]) {
+    const int64_t nv = n >> 1;
+    constexpr int64_t kTile = (int64_t)kThreads * U;
+    for (int64_t base = (int64_t)blockIdx.x * kTile; base < nv; base += (int64_t)gridDim.x * kTile) {
+        typename Op::Regs r[U];
+        if (base + kTile <= nv) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) op.load(r[u], base + u * kThreads + threadIdx.x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) op.apply(r[u], base + u * kThreads + threadIdx.x, acc);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + u * kThreads + threadIdx.x;
+                if (i < nv) op.load(r[u], i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + u * kThreads + threadIdx.x;
+                if (i < nv) op.apply(r[u], i, acc);
+            }
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.tail(n - 1, acc);
+}
+
+}  // namespace lb

@@ -1,0 +1,529 @@
+// solver.cpp — see solver.h.  Compiled by nvcc as host code with -ffp-contract=off.
+#include "solver.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace lb {
+
+namespace {
+constexpr int64_t kAlign = 256;  // bytes; every owned vector starts on a 256-byte boundary
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+}  // namespace
+
+int query_device(int device, DeviceInfo *out) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return LBFGSB200_ERR_CUDA;
+    int sm = 0, l2 = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    out->device = device;
+    out->sm_count = sm;
+    out->l2_bytes = l2;
+    out->blocks_per_sm = env_int("LBFGSB200_BLOCKS_PER_SM", 4);
+    if (out->blocks_per_sm < 1) out->blocks_per_sm = 1;
+    if (out->blocks_per_sm > 16) out->blocks_per_sm = 16;
+    return 0;
+}
+
+int alloc_reduce_ws(const DeviceInfo &info, ReduceWs *ws) {
+    ws->stride = info.sm_count * 16;
+    if (cudaMalloc((void **)&ws->partials, sizeof(double) * kMaxAcc * ws->stride) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (cudaMalloc((void **)&ws->ticket, 256) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (cudaMemset(ws->ticket, 0, 256) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    return 0;
+}
+void free_reduce_ws(ReduceWs *ws) {
+    if (ws->partials) cudaFree(ws->partials);
+    if (ws->ticket) cudaFree(ws->ticket);
+    ws->partials = nullptr;
+    ws->ticket = nullptr;
+}
+
+Solver::~Solver() {
+    for (auto &p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
+    for (auto e : event_pool_) cudaEventDestroy(e);
+    if (arena_) cudaFree(arena_);
+    if (scal_dev_) cudaFree(scal_dev_);
+    if (scal_host_) cudaFreeHost(scal_host_);
+    free_reduce_ws(&ws_);
+}
+
+int Solver::fail(int status, const char *msg) {
+    err_ = msg;
+    last_status_ = status;
+    return status;
+}
+int Solver::cuda_fail(cudaError_t e, const char *what) {
+    err_ = std::string(what) + ": " + cudaGetErrorString(e);
+    last_status_ = LBFGSB200_ERR_CUDA;
+    return LBFGSB200_ERR_CUDA;
+}
+
+int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, int64_t goff, int device,
+                 cudaStream_t stream, Comm *comm) {
+    if (p.struct_size != (int64_t)sizeof(lbfgsb200_param_t)) return fail(LBFGSB200_ERR_INVALID_PARAM, "param.struct_size mismatch");
+    if (n_local < 1 || n_global < n_local || goff < 0 || goff + n_local > n_global) return fail(LBFGSB200_ERR_INVALID_PARAM, "invalid shard geometry");
+    if (p.m < 1) return fail(LBFGSB200_ERR_INVALID_PARAM, "m must be >= 1");
+    // the builder's assert!s, src/lbfgs.rs:195,204,216,232,254,269,308,321,361
+    if (std::signbit(p.epsilon)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter epsilon specified.");
+    if (std::signbit(p.initial_inverse_hessian)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid beta parameter for scaling the initial step size.");
+    if (std::signbit(p.max_step_size)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid max_step_size parameter.");
+    if (!(p.ls_ftol >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter ftol specified.");
+    if (!(p.ls_gtol >= 0.0 && p.ls_gtol < 1.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter gtol specified.");
+    if (!(p.ls_xtol >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter xtol specified.");
+    if (!(p.ls_min_step >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter min_step specified.");
+    if (!(p.delta >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter delta specified.");
+    if (p.ls_algorithm < 0 || p.ls_algorithm > 3) return fail(LBFGSB200_ERR_INVALID_PARAM, "unknown line search algorithm");
+
+    p_ = p;
+    m_ = p.m;
+    n_ = n_local;
+    n_global_ = n_global;
+    goff_ = goff;
+    comm_ = comm;
+    stream_ = stream;
+    owl_ = p.orthantwise != 0;
+    if (owl_) {
+        if (std::signbit(p.owl_c)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter orthantwise c parameter specified.");
+        owl_start_ = p.owl_start;                                       // Orthantwise::start_end, orthantwise.rs:59-67
+        owl_end_ = (p.owl_end < 0) ? n_global : (p.owl_end < n_global ? p.owl_end : n_global);
+        if (!(owl_start_ < owl_end_)) return fail(LBFGSB200_ERR_INVALID_PARAM, "invalid start for orthantwise");
+    }
+    ls_.algorithm = (int)p.ls_algorithm;
+    ls_.ftol = p.ls_ftol;
+    ls_.gtol = p.ls_gtol;
+    ls_.xtol = p.ls_xtol;
+    ls_.min_step = p.ls_min_step;
+    ls_.max_step = p.ls_max_step;
+    ls_.max_linesearch = p.ls_max_linesearch;
+    ls_.gradient_only = p.ls_gradient_only != 0;
+
+    int rc = query_device(device, &dev_);
+    if (rc != 0) return fail(rc, "no usable CUDA device (this library has no CPU fallback)");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+
+    // One arena for every owned vector: x', g, gp, d, [pg], S[m], Y[m], [wp]
+    const int64_t vec_bytes = round_up(n_ * (int64_t)sizeof(double), kAlign);
+    const int64_t nvec = 4 + (owl_ ? 1 : 0) + 2 * m_;
+    const int64_t wp_bytes = owl_ ? round_up(n_, kAlign) : 0;
+    e = cudaMalloc(&arena_, (size_t)(nvec * vec_bytes + wp_bytes));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(arena)");
+    char *base = (char *)arena_;
+    auto take = [&]() { double *r = (double *)base; base += vec_bytes; return r; };
+    xbuf_[1] = take();
+    gbuf_[0] = take();
+    gbuf_[1] = take();
+    d_ = take();
+    if (owl_) pg_ = take();
+    S_.resize(m_);
+    Y_.resize(m_);
+    for (int64_t i = 0; i < m_; ++i) { S_[i] = take(); Y_[i] = take(); }
+    if (owl_) wp_ = (signed char *)base;
+    ys_.assign(m_, 0.0);
+
+    const size_t scal_bytes = sizeof(double) * (SLOT_COUNT * kMaxAcc + (size_t)m_);
+    e = cudaMalloc((void **)&scal_dev_, scal_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scalars)");
+    e = cudaMemset(scal_dev_, 0, scal_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(scalars)");
+    alpha_dev_ = scal_dev_ + SLOT_COUNT * kMaxAcc;
+    e = cudaMallocHost((void **)&scal_host_, sizeof(double) * kMaxAcc * 2);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+    rc = alloc_reduce_ws(dev_, &ws_);
+    if (rc != 0) return fail(rc, "cudaMalloc(reduce workspace)");
+
+    // evict-first accesses once the working set cannot live in L2
+    const double working_set = (double)(nvec + 1) * (double)vec_bytes;
+    streaming_ = working_set > 0.75 * (double)dev_.l2_bytes;
+    const int force = env_int("LBFGSB200_STREAMING", -1);
+    if (force == 0) streaming_ = false;
+    if (force == 1) streaming_ = true;
+    memset(&prof_, 0, sizeof(prof_));
+    return 0;
+}
+
+Launch Solver::launch_cfg() {
+    Launch L;
+    L.stream = stream_;
+    L.max_grid = dev_.sm_count * dev_.blocks_per_sm;
+    L.streaming = streaming_;
+    L.ws = ws_;
+    L.launch_counter = &launch_counter_;
+    return L;
+}
+
+// ---- instrumentation -----------------------------------------------------------------------
+void Solver::prof_begin(int kind) {
+    if (!timing_) return;
+    Pending p;
+    p.kind = kind;
+    for (cudaEvent_t *ev : {&p.a, &p.b}) {
+        if (!event_pool_.empty()) { *ev = event_pool_.back(); event_pool_.pop_back(); }
+        else cudaEventCreate(ev);
+    }
+    cudaEventRecord(p.a, stream_);
+    pending_.push_back(p);
+}
+void Solver::prof_end(int kind, double bytes) {
+    prof_.launches[kind] += 1;
+    prof_.bytes[kind] += bytes;
+    if (!timing_) return;
+    cudaEventRecord(pending_.back().b, stream_);
+}
+void Solver::prof_resolve() {
+    for (auto &p : pending_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) prof_.ms[p.kind] += ms;
+        event_pool_.push_back(p.a);
+        event_pool_.push_back(p.b);
+    }
+    pending_.clear();
+}
+void Solver::profile_get(lbfgsb200_profile_t *out) {
+    if (timing_) { cudaStreamSynchronize(stream_); prof_resolve(); }
+    *out = prof_;
+}
+void Solver::profile_reset() {
+    if (timing_) { cudaStreamSynchronize(stream_); prof_resolve(); }
+    memset(&prof_, 0, sizeof(prof_));
+}
+
+// ---- scalar plumbing ------------------------------------------------------------------------
+int Solver::reduce_across_ranks(int s, int count) {
+    if (!comm_ || comm_size(comm_) == 1) return 0;
+    prof_.allreduces += 1;
+    return comm_allreduce_sum(comm_, slot(s), count, stream_);
+}
+
+int Solver::fetch(int s, int count, double *host) {
+    int rc = reduce_across_ranks(s, count);
+    if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    cudaError_t e = cudaMemcpyAsync(scal_host_, slot(s), sizeof(double) * count, cudaMemcpyDeviceToHost, stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H scalars)");
+    e = cudaStreamSynchronize(stream_);
+    prof_.host_syncs += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if (timing_) prof_resolve();
+    for (int i = 0; i < count; ++i) host[i] = scal_host_[i];
+    return 0;
+}
+
+// Problem::evaluate (src/core.rs:119-132) followed by the reductions the driver needs at this
+// point: g.d for the line search, g.g (pg.pg) and x.x for Progress / the stop test.
+bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
+    const double *x = xbuf_[cur_x_];
+    double *g = gbuf_[cur_g_];
+    const double vbytes = 8.0 * (double)n_;
+    Launch L = launch_cfg();
+    double *sl = slot(SLOT_EVAL);
+
+    prof_begin(LBFGSB200_K_EVALUATE);
+    int erc = eval_(eval_user_, x, g, n_, (void *)stream_, sl + 0);
+    prof_end(LBFGSB200_K_EVALUATE, 0.0);
+    const bool multi = comm_ && comm_size(comm_) > 1;
+    if (erc != 0 && !multi) return false;
+
+    // OWL-QN with gradient_only is the one combination that needs g.d next to the pseudo-gradient
+    const bool want_gd = d_or_null != nullptr && (!owl_ || ls_.gradient_only);
+    if (owl_) {
+        prof_begin(LBFGSB200_K_OWL_PG);
+        launch_owl_pg(L, pg_, x, g, want_gd ? d_or_null : nullptr, n_, p_.owl_c, owl_start_, owl_end_, goff_, sl + 1);
+        prof_end(LBFGSB200_K_OWL_PG, (want_gd ? 4.0 : 3.0) * vbytes);
+    } else {
+        prof_begin(LBFGSB200_K_DOTS);
+        launch_dots(L, g, want_gd ? d_or_null : nullptr, x, n_, sl + 1);
+        prof_end(LBFGSB200_K_DOTS, (want_gd ? 3.0 : 2.0) * vbytes);
+    }
+    if (multi) {  // an Err on any rank must be seen by every rank (replicated control flow)
+        const double flag = erc != 0 ? 1.0 : 0.0;
+        scal_host_[kMaxAcc] = flag;
+        cudaMemcpyAsync(sl + 7, scal_host_ + kMaxAcc, sizeof(double), cudaMemcpyHostToDevice, stream_);
+    }
+    double h[kMaxAcc];
+    if (fetch(SLOT_EVAL, kMaxAcc, h) != 0) return false;
+    if (multi && h[7] != 0.0) return false;
+
+    neval_ += 1;
+    if (owl_) {
+        fx_ = h[0];
+        fx_ += h[1];        // fx += x1norm, core.rs:123-124
+        gg_ = h[2];
+        xx_ = h[3];
+        if (dg_out) *dg_out = h[4];
+    } else {
+        fx_ = h[0];
+        if (dg_out) *dg_out = h[1];
+        gg_ = h[2];
+        xx_ = h[3];
+    }
+    return true;
+}
+
+void Solver::fill_progress(lbfgsb200_progress_t *out, double step_value) const {  // core.rs:253-268
+    if (!out) return;
+    out->x_dev = xbuf_[cur_x_];
+    out->gx_dev = gbuf_[cur_g_];
+    out->n_local = n_;
+    out->n_global = n_global_;
+    out->fx = fx_;
+    out->xnorm = std::sqrt(xx_);
+    out->gnorm = std::sqrt(gg_);
+    out->step = step_value;
+    out->niter = k_;
+    out->neval = neval_;
+    out->ncall = ncall_;
+}
+
+// ---- Lbfgs::build, src/lbfgs.rs:443-481 ------------------------------------------------------
+int Solver::build(double *x_dev, lbfgsb200_eval_fn eval, void *user) {
+    if (!arena_) return fail(LBFGSB200_ERR_STATE, "solver not initialised");
+    if (!x_dev || !eval) return fail(LBFGSB200_ERR_INVALID_PARAM, "x_dev and eval must be non-null");
+    if (((uintptr_t)x_dev & 15u) != 0) return fail(LBFGSB200_ERR_INVALID_PARAM, "x_dev must be 16-byte aligned");
+    cudaError_t e = cudaSetDevice(dev_.device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    xbuf_[0] = x_dev;
+    cur_x_ = 0;
+    cur_g_ = 0;
+    eval_ = eval;
+    eval_user_ = user;
+    k_ = 0;
+    end_ = 0;
+    ncall_ = 0;
+    neval_ = 0;
+    last_ls_error_ = 0;
+    last_status_ = 0;
+    err_.clear();
+    built_ = false;
+
+    if (!evaluate_point(nullptr, nullptr)) {  // :454
+        if (last_status_ != 0) return last_status_;
+        return fail(LBFGSB200_ERR_EVALUATE, "evaluate failed at the initial point");
+    }
+    // d = -g (or -pg), :457; step = 1/||d|| * h0, :460-461
+    Launch L = launch_cfg();
+    prof_begin(LBFGSB200_K_INIT_DIR);
+    launch_init_dir(L, d_, owl_ ? pg_ : gbuf_[cur_g_], n_, slot(SLOT_INIT));
+    prof_end(LBFGSB200_K_INIT_DIR, 2.0 * 8.0 * (double)n_);
+    double h[2];
+    int rc = fetch(SLOT_INIT, 2, h);
+    if (rc != 0) return rc;
+    dginit_ = h[1];
+    step_ = (1.0 / std::sqrt(h[0])) * p_.initial_inverse_hessian;
+    built_ = true;
+    return 0;
+}
+
+// ---- satisfying_stop_conditions, src/lbfgs.rs:697-748 -----------------------------------------
+bool Solver::is_converged(int *stop_status) {
+    int st = -100;
+    if (p_.max_iterations != 0 && k_ >= p_.max_iterations) st = LBFGSB200_OK_MAX_ITERATIONS;
+    else if (p_.max_evaluations != 0 && neval_ >= p_.max_evaluations) st = LBFGSB200_OK_MAX_EVALUATIONS;
+    else if (std::sqrt(gg_) / std::fmax(std::sqrt(xx_), 1.0) <= p_.epsilon) st = LBFGSB200_OK_CONVERGED;
+    if (st == -100) return false;
+    if (stop_status) *stop_status = st;
+    return true;
+}
+
+// ---- LbfgsState::propagate, src/lbfgs.rs:503-560 ----------------------------------------------
+int Solver::propagate(lbfgsb200_progress_t *out) {
+    if (!built_) return fail(LBFGSB200_ERR_STATE, "propagate() before build()");
+    cudaError_t ce = cudaSetDevice(dev_.device);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+    k_ += 1;
+    if (k_ == 1) {  // :507-510
+        fill_progress(out, step_);
+        return 0;
+    }
+    Launch L = launch_cfg();
+    const double vbytes = 8.0 * (double)n_;
+
+    // save_state (core.rs:207-210) without moving a byte: the current buffers become xp / gp
+    const double *xp = xbuf_[cur_x_];
+    const double *gp = gbuf_[cur_g_];
+    const double xx_prev = xx_, gg_prev = gg_;
+    cur_x_ ^= 1;
+    cur_g_ ^= 1;
+    double *x = xbuf_[cur_x_];
+    double *g = gbuf_[cur_g_];
+    auto revert = [&]() {  // core.rs:201-204: x, gx restored; fx and pg are not
+        cur_x_ ^= 1;
+        cur_g_ ^= 1;
+        xx_ = xx_prev;
+        if (!owl_) gg_ = gg_prev;
+    };
+
+    // LineSearch::find, src/line.rs:193-223
+    LineSearchMachine ls;
+    if (ls.begin(ls_, owl_, fx_, dginit_, step_) != 0) {
+        revert();
+        return fail(LBFGSB200_ERR_LINESEARCH, "Failure during line search");
+    }
+    if (owl_) {  // update_orthant_new_point, line.rs:734-736
+        prof_begin(LBFGSB200_K_ORTHANT);
+        launch_orthant(L, wp_, xp, pg_, n_);
+        prof_end(LBFGSB200_K_ORTHANT, 2.0 * vbytes + (double)n_);
+    }
+    double stp = 0.0;
+    while (ls.next_trial(&stp)) {
+        prof_begin(LBFGSB200_K_TRIAL);  // take_line_step, core.rs:155-164
+        launch_trial(L, x, xp, d_, stp, n_, owl_ ? wp_ : nullptr, owl_start_, owl_end_, goff_);
+        prof_end(LBFGSB200_K_TRIAL, 3.0 * vbytes + (owl_ ? (double)n_ : 0.0));
+        double dg = 0.0;
+        const bool ok = evaluate_point(d_, &dg);
+        if (!ok && last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;  // CUDA / NCCL failure is fatal
+        ls.feed(ok, fx_, dg);
+    }
+    step_ = ls.step();
+    const double step_ls = step_;
+    if (ls.error() != 0 || ls.trials() == 0) {
+        // line.rs:213-220: revert and report Ok(0); x == xp then fails `ensure!(d != 0.0)` (lbfgs.rs:645).
+        // With max_linesearch <= 1 the loop body never runs and x was never moved: same outcome.
+        revert();
+        ncall_ = ls.error() != 0 ? 0 : ls.ncall();
+        if (ls.error() != 0) last_ls_error_ = ls.error();
+        char msg[96];
+        snprintf(msg, sizeof(msg), "x not changed with step %g", step_);
+        return fail(LBFGSB200_ERR_X_NOT_CHANGED, msg);
+    }
+    ncall_ = ls.ncall();
+
+    // IterationData::update, src/lbfgs.rs:640-692
+    const int64_t slot_new = end_;
+    const bool damping = p_.damping != 0;
+    prof_begin(LBFGSB200_K_HISTORY);
+    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, slot(SLOT_HIST));
+    prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
+    double h[5];
+    int rc = fetch(SLOT_HIST, 5, h);
+    if (rc != 0) return rc;
+    const double ss = h[0], ys = h[1], yy = h[2], sbs = h[4];
+    if (!(std::sqrt(ss) != 0.0)) {  // :645-646
+        char msg[96];
+        snprintf(msg, sizeof(msg), "x not changed with step %g", step_);
+        return fail(LBFGSB200_ERR_X_NOT_CHANGED, msg);
+    }
+    if (!(yy != 0.0)) return fail(LBFGSB200_ERR_G_NOT_CHANGED, "gx not changed");  // :655
+    ys_[slot_new] = ys;
+    if (damping) {  // :664-689
+        const double sigma2 = 0.6, sigma3 = 3.0;
+        if (ys < (1.0 - sigma2) * sbs) {  // case 1: y is replaced
+            const double theta = sigma2 * sbs / (sbs - ys);
+            prof_begin(LBFGSB200_K_DAMP);
+            launch_damp(L, Y_[slot_new], gp, n_, -step_, 1.0 - theta, theta);
+            prof_end(LBFGSB200_K_DAMP, 3.0 * vbytes);
+        } else if (ys > (1.0 + sigma3) * sbs) {
+            // case 2 computes a damped vector and drops it (:681-685): y stays as it is
+        }
+    }
+    const double gamma = ys / yy;  // :691
+
+    // lbfgs_two_loop_recursion, src/lbfgs.rs:569-604, one fused kernel per trip
+    end_ = (end_ + 1) % m_;
+    const int64_t bound = (m_ < k_ - 1) ? m_ : (k_ - 1);
+    int64_t j = end_;
+    const double *red_in = slot(SLOT_HIST) + 3;  // s_new . (-g), produced by the history kernel
+    int pp = 0;
+    const double *dsrc = owl_ ? pg_ : g;          // d = -g | -pg, core.rs:95-101
+    for (int64_t t = 0; t < bound; ++t) {
+        j = (j + m_ - 1) % m_;
+        const bool first = (t == 0), last = (t == bound - 1);
+        const int64_t jn = (j + m_ - 1) % m_;
+        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
+        prof_begin(LBFGSB200_K_BACKWARD);
+        launch_backward(L, first, last, d_, dsrc, Y_[j], last ? nullptr : S_[jn], n_, red_in, ys_[j], gamma, alpha_dev_ + j, slot(so));
+        prof_end(LBFGSB200_K_BACKWARD, (last ? 3.0 : 4.0) * vbytes);
+        rc = reduce_across_ranks(so, 1);
+        if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        red_in = slot(so);
+        pp ^= 1;
+    }
+    int so_last = SLOT_LOOP_A;
+    for (int64_t t = 0; t < bound; ++t) {
+        const bool last = (t == bound - 1);
+        const int64_t jn = (j + 1) % m_;
+        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
+        prof_begin(LBFGSB200_K_FORWARD);
+        launch_forward(L, last, owl_, d_, S_[j], last ? nullptr : Y_[jn], dsrc, n_, red_in, ys_[j], alpha_dev_ + j,
+                       owl_start_, owl_end_, goff_, slot(so));
+        prof_end(LBFGSB200_K_FORWARD, 4.0 * vbytes);
+        if (!last) {
+            rc = reduce_across_ranks(so, 1);
+            if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        }
+        red_in = slot(so);
+        so_last = so;
+        pp ^= 1;
+        j = jn;
+    }
+    double hd[3];
+    rc = fetch(so_last, 3, hd);
+    if (rc != 0) return rc;
+    const double dnorm = std::sqrt(hd[0]);  // :543 (before the orthant projection)
+    dginit_ = hd[1];
+    if (std::signbit(dnorm)) return fail(LBFGSB200_ERR_INVALID_DNORM, "invalid norm value");  // :544
+    if (p_.constrain_step_size) step_ = std::fmin(p_.max_step_size, dnorm) / dnorm;        // :547-551
+    else step_ = 1.0;
+    if (owl_ && !(std::sqrt(hd[2]) != 0.0))                                                  // orthantwise.rs:160
+        return fail(LBFGSB200_ERR_OWLQN_ZERO_DIRECTION, "invalid direction vector after constraints");
+
+    fill_progress(out, step_ls);  // :556-557
+    return 0;
+}
+
+void Solver::report(lbfgsb200_report_t *out) const {
+    if (!out) return;
+    out->fx = fx_;
+    out->xnorm = std::sqrt(xx_);
+    out->gnorm = std::sqrt(gg_);
+    out->neval = neval_;
+    out->niter = k_;
+    out->last_ls_error = last_ls_error_;
+    out->status = last_status_;
+}
+
+int Solver::finish() {
+    if (cur_x_ != 0 && xbuf_[0]) {
+        cudaError_t e = cudaMemcpyAsync(xbuf_[0], xbuf_[1], sizeof(double) * (size_t)n_, cudaMemcpyDeviceToDevice, stream_);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2D x)");
+        // keep the roles consistent: the caller's buffer is current again, ours holds the copy
+        cur_x_ = 0;
+    }
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if (timing_) prof_resolve();
+    return 0;
+}
+
+// ---- Lbfgs::minimize, src/lbfgs.rs:399-421 -----------------------------------------------------
+int Solver::minimize(double *x_dev, lbfgsb200_eval_fn eval, void *user, lbfgsb200_progress_fn prog, void *prog_user,
+                     lbfgsb200_report_t *rep) {
+    int rc = build(x_dev, eval, user);
+    if (rc != 0) {
+        report(rep);
+        return rc;
+    }
+    int status = 0;
+    for (;;) {
+        int st = 0;
+        if (is_converged(&st)) { status = st; break; }
+        lbfgsb200_progress_t pr;
+        rc = propagate(&pr);
+        if (rc != 0) { status = rc; break; }
+        if (prog && prog(prog_user, &pr) != 0) { status = LBFGSB200_OK_CANCELLED; break; }
+    }
+    int frc = finish();
+    if (frc != 0 && status >= 0) status = frc;
+    last_status_ = status;
+    report(rep);
+    return status;
+}
+
+}  // namespace lb

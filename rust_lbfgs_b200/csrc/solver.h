@@ -1,0 +1,129 @@
+// solver.h — the device-resident L-BFGS / OWL-QN driver (host side).
+//
+// `Solver` is what `Problem` (src/core.rs:10-75) + `LbfgsState` (src/lbfgs.rs:425-439) become when
+// every n-vector lives in HBM: it owns g/gp (ping-pong), the second x buffer, d, pg, wp and the
+// 2m-vector s/y ring, launches the fused kernels of kernels.cu on one stream, and keeps only
+// scalars on the host.  The host synchronises where the scalar logic needs a value: once per
+// line-search trial (f, dg), once after the history update (ys, yy for the error checks / damping)
+// and once after the two-loop (||d|| for the next step).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lbfgsb200.h"
+#include "kernels.h"
+#include "linesearch.h"
+
+namespace lb {
+
+struct Comm;
+int comm_rank(const Comm *c);
+int comm_size(const Comm *c);
+int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream);
+
+// Launch configuration for a device (SM count, L2 size, env overrides); shared by the solver,
+// the stand-alone primitives and the built-in objectives.
+struct DeviceInfo {
+    int device = 0;
+    int sm_count = 148;
+    int64_t l2_bytes = 126ll << 20;
+    int blocks_per_sm = 4;
+};
+int query_device(int device, DeviceInfo *out);
+// allocates the level-2 reduction workspace for `info`
+int alloc_reduce_ws(const DeviceInfo &info, ReduceWs *ws);
+void free_reduce_ws(ReduceWs *ws);
+
+class Solver {
+  public:
+    Solver() = default;
+    ~Solver();
+    int init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, int64_t goff, int device,
+             cudaStream_t stream, Comm *comm);
+
+    int build(double *x_dev, lbfgsb200_eval_fn eval, void *user);          // src/lbfgs.rs:443-481
+    bool is_converged(int *stop_status);                                   // :489-494, :697-748
+    int propagate(lbfgsb200_progress_t *out);                              // :503-560
+    void report(lbfgsb200_report_t *out) const;                            // src/core.rs:288-298
+    int finish();
+    int minimize(double *x_dev, lbfgsb200_eval_fn eval, void *user, lbfgsb200_progress_fn prog, void *prog_user,
+                 lbfgsb200_report_t *rep);                                 // src/lbfgs.rs:399-421
+
+    const double *x() const { return xbuf_[cur_x_]; }
+    const double *gx() const { return gbuf_[cur_g_]; }
+    const double *direction() const { return d_; }
+    const std::string &error() const { return err_; }
+
+    void profile_enable(bool timing) { timing_ = timing; }
+    void profile_get(lbfgsb200_profile_t *out);
+    void profile_reset();
+
+  private:
+    // scalar slots in device memory (kMaxAcc doubles each)
+    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_COUNT = 5 };
+    double *slot(int s) const { return scal_dev_ + (size_t)s * kMaxAcc; }
+
+    int fail(int status, const char *msg);
+    int cuda_fail(cudaError_t e, const char *what);
+    bool evaluate_point(const double *d_or_null, double *dg_out);  // evaluate + K2/K3 + allreduce + sync
+    int fetch(int s, int count, double *host);                     // allreduce + D2H + sync of a slot
+    int reduce_across_ranks(int s, int count);
+    void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
+    Launch launch_cfg();
+
+    // timing instrumentation
+    struct Pending { int kind; cudaEvent_t a, b; };
+    void prof_begin(int kind);
+    void prof_end(int kind, double bytes);
+    void prof_resolve();
+
+    lbfgsb200_param_t p_{};
+    LsConfig ls_{};
+    bool owl_ = false;
+    int64_t owl_start_ = 0, owl_end_ = 0;
+    int64_t n_ = 0, n_global_ = 0, goff_ = 0;
+    int64_t m_ = 6;
+    DeviceInfo dev_{};
+    cudaStream_t stream_ = nullptr;
+    Comm *comm_ = nullptr;
+    bool streaming_ = true;
+
+    // HBM
+    void *arena_ = nullptr;
+    double *xbuf_[2] = {nullptr, nullptr};  // [0] = caller's x, [1] = ours
+    double *gbuf_[2] = {nullptr, nullptr};
+    double *d_ = nullptr, *pg_ = nullptr;
+    signed char *wp_ = nullptr;
+    std::vector<double *> S_, Y_;
+    double *scal_dev_ = nullptr;    // SLOT_COUNT * kMaxAcc doubles, then alpha[m]
+    double *alpha_dev_ = nullptr;
+    double *scal_host_ = nullptr;   // pinned mirror of one slot
+    ReduceWs ws_{};
+    int cur_x_ = 0, cur_g_ = 0;
+
+    // host scalars
+    lbfgsb200_eval_fn eval_ = nullptr;
+    void *eval_user_ = nullptr;
+    bool built_ = false;
+    double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point
+    double dginit_ = 0.0;                      // g.d (pg.d) for the next line search
+    double step_ = 0.0;
+    int64_t k_ = 0, end_ = 0, ncall_ = 0, neval_ = 0;
+    int64_t last_ls_error_ = 0;
+    int last_status_ = 0;
+    std::vector<double> ys_;
+    std::string err_;
+
+    // profile
+    bool timing_ = false;
+    lbfgsb200_profile_t prof_{};
+    std::vector<Pending> pending_;
+    std::vector<cudaEvent_t> event_pool_;
+    int64_t launch_counter_ = 0;
+};
+
+}  // namespace lb

@@ -1,0 +1,84 @@
+"""Built-in device-resident objectives (csrc/objectives.cu), usable as `evaluate` in Lbfgs.minimize.
+
+Each wraps an lbfgsb200_objective_t; `lbfgsb200_objective_eval` is the lbfgsb200_eval_fn and the
+handle is its `user` pointer, so a solve never calls back into Python.
+"""
+import ctypes as C
+
+from . import _lib
+
+
+class _Builtin:
+    def __init__(self):
+        self._handles = {}
+
+    def _create(self, L, device, out):
+        raise NotImplementedError
+
+    def _eval_ptr(self):
+        return C.cast(_lib.lib().lbfgsb200_objective_eval, C.c_void_p)
+
+    def _user_ptr(self, device):
+        if device not in self._handles:
+            L = _lib.lib()
+            out = C.c_void_p()
+            st = self._create(L, device, out)
+            if st != 0:
+                raise RuntimeError(f"creating objective failed: {_lib.STATUS_NAMES.get(st, st)}")
+            self._handles[device] = out
+        return self._handles[device]
+
+    def close(self):
+        L = _lib.lib()
+        for h in self._handles.values():
+            L.lbfgsb200_objective_destroy(h)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Rosenbrock(_Builtin):
+    """default_evaluate(), src/lib.rs:79-94 (len(x) must be even)."""
+
+    def _create(self, L, device, out):
+        return L.lbfgsb200_objective_rosenbrock(device, C.byref(out))
+
+
+class Booth(_Builtin):
+    """tests/simple.rs:65-74 (n = 2)."""
+
+    def _create(self, L, device, out):
+        return L.lbfgsb200_objective_booth(device, C.byref(out))
+
+
+class Glm(_Builtin):
+    """Dense GLM objective; X (nrow x ncol, row-major) and y are float64 CUDA tensors kept alive here.
+
+    kind="poisson": tests/owlqn.rs:22-43; kind="logistic": BASELINE.json configs[2]."""
+
+    def __init__(self, kind, X, y):
+        super().__init__()
+        self.kind = {"poisson": 0, "logistic": 1}[kind]
+        assert X.is_cuda and y.is_cuda and X.is_contiguous() and y.is_contiguous()
+        assert str(X.dtype) == "torch.float64" and str(y.dtype) == "torch.float64"
+        assert X.dim() == 2 and y.numel() == X.shape[0]
+        self.X, self.y = X, y
+
+    def _create(self, L, device, out):
+        return L.lbfgsb200_objective_glm(device, self.kind, self.X.data_ptr(), self.y.data_ptr(),
+                                         self.X.shape[0], self.X.shape[1], C.byref(out))
+
+
+class LennardJones(_Builtin):
+    """examples/lj.rs:20-64,114-117: all-pairs LJ energy and gradient, x = 3 * atoms."""
+
+    def __init__(self, epsilon=1.0, sigma=1.0):
+        super().__init__()
+        self.epsilon, self.sigma = float(epsilon), float(sigma)
+
+    def _create(self, L, device, out):
+        return L.lbfgsb200_objective_lennard_jones(device, self.epsilon, self.sigma, C.byref(out))

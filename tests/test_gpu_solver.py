@@ -1,0 +1,272 @@
+"""The CUDA solver against the oracle on the reference's own test problems and beyond (through the
+Python mirror of the builder API, i.e. the C ABI).
+
+Bar (BASELINE.json north_star): identical termination status and iteration count, identical
+per-iteration evaluation counts, identical OWL-QN orthant sign patterns, x and fx within 1e-10
+relative per iteration over the first 50 iterations and 1e-8 at convergence.
+fx is compared relative to max(|fx|, 1e-12 * |fx_0|): near a zero minimum the relative error of fx
+is not defined by the solver's accuracy (SURVEY.md §7 "Relative fx error near fx -> 0")."""
+import os
+
+import numpy as np
+import pytest
+
+import rust_lbfgs_b200 as R
+from gpu_util import compare_traces, gpu_minimize, host
+from util import rosenbrock_x0
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_run(oracle, x0, objective, **kw):
+    return oracle.minimize(oracle.default_param(**kw), np.asarray(x0, dtype=np.float64).copy(), objective,
+                           record_x=True)
+
+
+# ---- P2 / P3: tests/simple.rs:17-55 ------------------------------------------------------------------
+def test_p2_rosenbrock_n100_defaults(oracle):
+    ref = oracle_run(oracle, rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"))
+    got = gpu_minimize(R.lbfgs(), rosenbrock_x0(100), R.Rosenbrock())
+    worst = compare_traces(ref, got)
+    print("worst rel err", worst)
+    assert got["status_name"] == "OK_CONVERGED" and len(got["trace"]) == 35 and got["report"].neval == 40
+    assert abs(got["report"].fx) <= 1e-4 and np.all(np.abs(got["x"] - 1.0) <= 1e-4)   # tests/simple.rs:37-40
+
+
+def test_p3_owlqn_follow_up(oracle):
+    first = oracle_run(oracle, rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"))
+    x1 = first["x"]
+    ref = oracle_run(oracle, x1, oracle.Objective.builtin("rosenbrock"), orthantwise=1, owl_c=1.0, owl_start=0, owl_end=99)
+    got = gpu_minimize(R.lbfgs().with_orthantwise(1.0, 0, 99), x1, R.Rosenbrock())
+    compare_traces(ref, got, first=50)
+    assert len(got["trace"]) == 150 and got["report"].neval == 338
+    assert abs(got["report"].fx - 43.5025) <= 1e-4                                   # tests/simple.rs:52
+    assert abs(got["x"][0] - 0.25) <= 1e-4 and abs(got["x"][1] - 0.0575) <= 1e-4      # tests/simple.rs:53-54
+    for a, b in zip(ref["trace"], got["trace"]):                                      # orthant sign patterns
+        assert np.array_equal(np.sign(a["x"]), np.sign(b["x"]))
+
+
+# ---- P4: tests/simple.rs:57-83 -------------------------------------------------------------------------
+def test_p4_booth(oracle):
+    ref = oracle_run(oracle, [-1.2, 1.0], oracle.Objective.builtin("booth"))
+    got = gpu_minimize(R.lbfgs(), [-1.2, 1.0], R.Booth())
+    compare_traces(ref, got)
+    assert abs(got["x"][0] - 1.0) <= 1e-6 and abs(got["x"][1] - 3.0) <= 1e-6
+
+
+def test_p4_booth_python_callable_evaluate(oracle):
+    """A user-written device evaluate (torch ops on the views) instead of a built-in objective."""
+    def booth(x, gx):
+        x1, x2 = x[0], x[1]
+        gx[0] = 10.0 * x1 + 8.0 * x2 - 34.0
+        gx[1] = 8.0 * x1 + 10.0 * x2 - 38.0
+        return (x1 + 2.0 * x2 - 7.0) ** 2 + (2.0 * x1 + x2 - 5.0) ** 2
+    got = gpu_minimize(R.lbfgs(), [-1.2, 1.0], booth)
+    assert got["status_name"] == "OK_CONVERGED"
+    assert abs(got["x"][0] - 1.0) <= 1e-6 and abs(got["x"][1] - 3.0) <= 1e-6
+
+
+# ---- P5: tests/owlqn.rs:5-63 ------------------------------------------------------------------------------
+def test_p5_owlqn_poisson_fixture(oracle, golden_dir):
+    from gpu_util import dev
+    d = np.load(os.path.join(golden_dir, "poisson_500x21.npz"))
+    got = gpu_minimize(R.lbfgs().with_orthantwise(1.0, 1, 21).with_epsilon(1e-4), np.zeros(21),
+                       R.Glm("poisson", dev(d["X"]), dev(d["y"])))
+    assert got["status_name"] == "OK_CONVERGED"
+    assert abs(got["report"].fx - (-42724.136705)) <= 1e-6                            # tests/owlqn.rs:60
+    # the well-conditioned part of the trajectory follows the oracle (the tail works at the rounding
+    # level of fx ~ 4e4 * 2^-52 and depends on the objective's summation order)
+    ref = oracle_run(oracle, np.zeros(21), oracle.Objective.glm("poisson", d["X"], d["y"]), orthantwise=1,
+                     owl_c=1.0, owl_start=1, owl_end=21, epsilon=1e-4)
+    for a, b in list(zip(ref["trace"], got["trace"]))[:40]:
+        assert a["ncall"] == b["ncall"]
+        assert abs(a["fx"] - b["fx"]) <= 1e-10 * abs(a["fx"])
+        assert np.max(np.abs(a["x"] - b["x"])) <= 1e-8 * max(np.max(np.abs(a["x"])), 1e-300)
+        assert np.array_equal(np.sign(a["x"]), np.sign(b["x"]))
+
+
+# ---- every line search, damping, gradient-only ---------------------------------------------------------------
+@pytest.mark.parametrize("algo,name", [(0, "MoreThuente"), (1, "BacktrackingArmijo"), (2, "BacktrackingWolfe"),
+                                       (3, "BacktrackingStrongWolfe")])
+def test_linesearch_algorithms(oracle, algo, name):
+    ref = oracle_run(oracle, rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"), ls_algorithm=algo)
+    got = gpu_minimize(R.lbfgs().with_linesearch_algorithm(name), rosenbrock_x0(100), R.Rosenbrock())
+    compare_traces(ref, got)
+
+
+@pytest.mark.parametrize("n", [2, 10, 1000, 10000, 100000])
+def test_rosenbrock_sizes(oracle, n):
+    ref = oracle_run(oracle, rosenbrock_x0(n), oracle.Objective.builtin("rosenbrock"))
+    got = gpu_minimize(R.lbfgs(), rosenbrock_x0(n), R.Rosenbrock())
+    compare_traces(ref, got)
+
+
+def test_damping_and_gradient_only_lj38(oracle, golden_dir):
+    """examples/lj.rs; with_damping / with_gradient_only (src/lbfgs.rs:223-227,283-289); quirk 12."""
+    p0 = np.load(os.path.join(golden_dir, "lj38.npy")).ravel()
+    lj = oracle.Objective.builtin("lj")
+    for kw, b in (
+        (dict(), R.lbfgs()),
+        (dict(damping=1), R.lbfgs().with_damping(True)),
+        (dict(ls_gradient_only=1, damping=1, ls_algorithm=3), R.lbfgs().with_gradient_only()),
+        (dict(ls_gradient_only=1, damping=1, ls_algorithm=3, ls_max_linesearch=2),
+         R.lbfgs().with_gradient_only().with_max_linesearch(2)),
+    ):
+        ref = oracle_run(oracle, p0, lj, max_iterations=60, **kw)
+        got = gpu_minimize(b.with_max_iterations(60), p0, R.LennardJones())
+        compare_traces(ref, got, tol_iter=1e-9, first=60)
+
+
+def test_damping_changes_trajectory_like_oracle(oracle):
+    """Powell damping case 1 must actually fire somewhere and still match (src/lbfgs.rs:675-680)."""
+    x0 = rosenbrock_x0(50) * np.linspace(0.5, 1.5, 50)
+    plain = oracle_run(oracle, x0, oracle.Objective.builtin("rosenbrock"), ls_algorithm=1, max_iterations=40)
+    damped = oracle_run(oracle, x0, oracle.Objective.builtin("rosenbrock"), ls_algorithm=1, damping=1, max_iterations=40)
+    got = gpu_minimize(R.lbfgs().with_linesearch_algorithm("BacktrackingArmijo").with_damping(True)
+                       .with_max_iterations(40), x0, R.Rosenbrock())
+    compare_traces(damped, got, first=40)
+    assert any(not np.array_equal(a["x"], b["x"]) for a, b in zip(plain["trace"], damped["trace"]))
+
+
+# ---- stop conditions, cancel, errors ----------------------------------------------------------------------------
+def test_stop_conditions_and_cancel(oracle):
+    ros = oracle.Objective.builtin("rosenbrock")
+    for kw, b in ((dict(max_iterations=5), R.lbfgs().with_max_iterations(5)),
+                  (dict(max_evaluations=10), R.lbfgs().with_max_evaluations(10)),
+                  (dict(epsilon=1e-2), R.lbfgs().with_epsilon(1e-2)),
+                  (dict(max_step_size=0.1), R.lbfgs().with_max_step_size(0.1)),
+                  (dict(initial_inverse_hessian=0.01), R.lbfgs().with_initial_step_size(0.01)),
+                  (dict(ls_gtol=0.1), R.lbfgs().with_linesearch_gtol(0.1)),
+                  (dict(m=3), R.lbfgs().with_m(3)), (dict(m=20), R.lbfgs().with_m(20))):
+        ref = oracle_run(oracle, rosenbrock_x0(100), ros, **kw)
+        got = gpu_minimize(b, rosenbrock_x0(100), R.Rosenbrock())
+        compare_traces(ref, got)
+    ref = oracle.minimize(oracle.default_param(), rosenbrock_x0(100), ros, record_x=True, progress=lambda r: r["niter"] == 4)
+    got = gpu_minimize(R.lbfgs(), rosenbrock_x0(100), R.Rosenbrock(), progress=lambda r: r["niter"] == 4)
+    assert got["status_name"] == ref["status_name"] == "OK_CANCELLED"
+    compare_traces(ref, got)
+
+
+def test_error_paths_match_reference_semantics(oracle):
+    ros = oracle.Objective.builtin("rosenbrock")
+    # quirk 12: max_linesearch 0/1 never evaluates a trial => "x not changed" (src/lbfgs.rs:645-646)
+    for ml in (0, 1):
+        ref = oracle_run(oracle, rosenbrock_x0(100), ros, ls_max_linesearch=ml)
+        got = gpu_minimize(R.lbfgs().with_max_linesearch(ml), rosenbrock_x0(100), R.Rosenbrock())
+        assert got["status_name"] == ref["status_name"] == "ERR_X_NOT_CHANGED"
+        assert np.array_equal(got["x"], rosenbrock_x0(100))
+    # evaluate Err at the initial point propagates (src/lbfgs.rs:454)
+    got = gpu_minimize(R.lbfgs(), rosenbrock_x0(10), lambda x, g: None)
+    assert got["status_name"] == "ERR_EVALUATE"
+    # evaluate Err inside a search is swallowed, the point reverted, then "x not changed" (src/line.rs:213-220)
+    calls = {"n": 0}
+
+    def flaky(x, g):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            return None
+        t1 = 1.0 - x[0::2]
+        t2 = 10.0 * (x[1::2] - x[0::2] * x[0::2])
+        g[1::2] = 20.0 * t2
+        g[0::2] = -2.0 * (x[0::2] * g[1::2] + t1)
+        return (t1 * t1 + t2 * t2).sum()
+    got = gpu_minimize(R.lbfgs(), rosenbrock_x0(10), flaky)
+    assert got["status_name"] == "ERR_X_NOT_CHANGED" and got["report"].last_ls_error == 1
+    # gradient-only + MoreThuente: Err out of find (src/line.rs:208)
+    got = gpu_minimize(R.lbfgs().with_gradient_only().with_linesearch_algorithm("MoreThuente"), rosenbrock_x0(10), R.Rosenbrock())
+    assert got["status_name"] == "ERR_LINESEARCH"
+    # invalid OWL-QN range panics in the reference (src/orthantwise.rs:64)
+    with pytest.raises(ValueError):
+        gpu_minimize(R.lbfgs().with_orthantwise(1.0, 5, 3), rosenbrock_x0(10), R.Rosenbrock())
+    # odd n for Rosenbrock: the reference would index out of bounds; here evaluate returns Err
+    got = gpu_minimize(R.lbfgs(), np.ones(7), R.Rosenbrock())
+    assert got["status_name"] == "ERR_EVALUATE"
+
+
+def test_iterative_api_matches_minimize(oracle):
+    """build / is_converged / propagate / report (src/lbfgs.rs:443-566)."""
+    import torch
+    x = torch.tensor(rosenbrock_x0(100), device="cuda:0")
+    st = R.lbfgs().build(x, R.Rosenbrock())
+    n = 0
+    while not st.is_converged():
+        p = st.propagate()
+        n += 1
+        assert p.niter == n
+    st.finish()
+    rep = st.report()
+    ref = oracle_run(oracle, rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"))
+    assert n == len(ref["trace"]) and rep.neval == ref["report"]["neval"]
+    assert np.max(np.abs(host(x) - ref["x"])) <= 1e-8
+    assert st.stop_status == 0
+
+
+def test_owlqn_partial_range_and_odd_sizes(oracle):
+    """OWL-QN with start > 0, end < n, and an odd-length vector (scalar tail path) on a separable objective."""
+    n = 1001
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0.5, 2.0, n)
+    b = rng.standard_normal(n)
+
+    def f_np(x, g):
+        g[:] = a * (x - b)
+        return float(np.sum(0.5 * a * (x - b) ** 2))
+
+    def f_t(x, g):
+        import torch
+        at = torch.as_tensor(a, device=x.device)
+        bt = torch.as_tensor(b, device=x.device)
+        g.copy_(at * (x - bt))
+        return (0.5 * at * (x - bt) ** 2).sum()
+    ref = oracle_run(oracle, np.zeros(n), oracle.Objective.python(f_np), orthantwise=1, owl_c=0.5, owl_start=3, owl_end=900)
+    got = gpu_minimize(R.lbfgs().with_orthantwise(0.5, 3, 900), np.zeros(n), f_t)
+    assert got["status_name"] == ref["status_name"]
+    assert abs(len(got["trace"]) - len(ref["trace"])) <= 2
+    assert abs(got["report"].fx - ref["report"]["fx"]) <= 1e-9 * abs(ref["report"]["fx"])
+    assert np.array_equal(np.sign(got["x"]), np.sign(ref["x"]))
+    assert np.max(np.abs(got["x"] - ref["x"])) <= 1e-6
+
+
+# ---- large n: reduction accuracy and full-size invariants ------------------------------------------------------------
+def test_rosenbrock_4m_against_compensated_oracle(oracle):
+    """At n >= 1e6 the reference's sequential sums are themselves off by ~1e-10..1e-9; compare status, counts and
+    per-iteration ncall with the faithful oracle and x / fx with the compensated-sum oracle."""
+    n = 1 << 22
+    kw = dict(max_iterations=16)
+    faithful = oracle_run(oracle, rosenbrock_x0(n), oracle.Objective.builtin("rosenbrock"), **kw)
+    accurate = oracle_run(oracle, rosenbrock_x0(n), oracle.Objective.builtin("rosenbrock", 1), reduction_mode=1, **kw)
+    got = gpu_minimize(R.lbfgs().with_max_iterations(16), rosenbrock_x0(n), R.Rosenbrock())
+    assert got["status_name"] == faithful["status_name"] == "OK_MAX_ITERATIONS"
+    assert [t["ncall"] for t in got["trace"]] == [t["ncall"] for t in faithful["trace"]]
+    compare_traces(accurate, got, tol_iter=1e-10, first=16)
+
+
+def test_full_size_invariants_n1e8():
+    """BASELINE.json configs[1] at full size.  With x0 = (-1.2, 1.0) repeated every pair sees identical scalars,
+    so all pairs must stay bit-identical, fx must equal (n/2) * f_pair and ||x||^2 = (n/2)(x0^2 + x1^2): a
+    size-independent check of the fused kernels and the two-level reductions at n = 1e8."""
+    import torch
+    n = 100_000_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 19 * 8 * n * 1.05:
+        pytest.skip("not enough free HBM")
+    x = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    x[0::2] = -1.2
+    x[1::2] = 1.0
+    st = R.lbfgs().build(x, R.Rosenbrock())
+    fx_prev = None
+    for k in range(6):
+        p = st.propagate()
+        xv = p.x
+        x0, x1 = float(xv[0]), float(xv[1])
+        assert bool((xv[0::2] == x0).all()) and bool((xv[1::2] == x1).all())
+        t1, t2 = 1.0 - x0, 10.0 * (x1 - x0 * x0)
+        f_pair = t1 * t1 + t2 * t2
+        assert abs(p.fx - (n // 2) * f_pair) <= 1e-12 * abs(p.fx)
+        assert abs(p.xnorm ** 2 - (n // 2) * (x0 * x0 + x1 * x1)) <= 1e-12 * p.xnorm ** 2
+        gv = p.gx
+        assert abs(p.gnorm ** 2 - (n // 2) * (float(gv[0]) ** 2 + float(gv[1]) ** 2)) <= 1e-12 * p.gnorm ** 2
+        if fx_prev is not None:
+            assert p.fx < fx_prev
+        fx_prev = p.fx
+    st.close()
