@@ -124,16 +124,16 @@ def test_trial_step_and_owl_ops_bit_exact(oracle, n):
     start, end = (1 if n > 2 else 0), max(n - 1, 1)
     c = 0.9
 
-    # plain trial step
-    xd = dev(np.zeros(n))
-    ck(L.lbfgsb200_trial_step(xd.data_ptr(), dev(xp).data_ptr(), dev(d).data_ptr(), step, n, None, 0, 0, stream()))
+    # plain trial step (keep every device tensor referenced while kernels use its pointer)
+    xd, xpd, dvd, gvd = dev(np.zeros(n)), dev(xp), dev(d), dev(g)
+    ck(L.lbfgsb200_trial_step(xd.data_ptr(), xpd.data_ptr(), dvd.data_ptr(), step, n, None, 0, 0, stream()))
     xr = xp.copy(); O.oracle_vecadd(xr, d, step, n)
     assert np.array_equal(host(xd), xr)
 
     # pseudo-gradient + l1 + norms
     pgd = dev(np.zeros(n))
     out = (C.c_double * 3)()
-    ck(L.lbfgsb200_owl_pseudo_gradient(pgd.data_ptr(), dev(xp).data_ptr(), dev(g).data_ptr(), n, c, start, end,
+    ck(L.lbfgsb200_owl_pseudo_gradient(pgd.data_ptr(), xpd.data_ptr(), gvd.data_ptr(), n, c, start, end,
                                        stream(), out))
     pgr = np.zeros(n); O.oracle_owl_pseudo_gradient(pgr, xp, g, n, c, start, end)
     assert np.array_equal(host(pgd), pgr)
@@ -144,12 +144,12 @@ def test_trial_step_and_owl_ops_bit_exact(oracle, n):
 
     # orthant selection (int8 on device, f64 in the reference)
     wpd = torch.zeros(n + (n & 1), dtype=torch.int8, device="cuda:0")
-    ck(L.lbfgsb200_owl_orthant(wpd.data_ptr(), dev(xp).data_ptr(), pgd.data_ptr(), n, stream()))
+    ck(L.lbfgsb200_owl_orthant(wpd.data_ptr(), xpd.data_ptr(), pgd.data_ptr(), n, stream()))
     wpr = np.zeros(n); O.oracle_owl_orthant(wpr, xp, pgr, n)
     assert np.array_equal(host(wpd)[:n].astype(np.float64), wpr)
 
     # projected trial step
-    ck(L.lbfgsb200_trial_step(xd.data_ptr(), dev(xp).data_ptr(), dev(d).data_ptr(), step, n, wpd.data_ptr(), start,
+    ck(L.lbfgsb200_trial_step(xd.data_ptr(), xpd.data_ptr(), dvd.data_ptr(), step, n, wpd.data_ptr(), start,
                               end, stream()))
     xr = xp.copy(); O.oracle_vecadd(xr, d, step, n); O.oracle_owl_project(xr, wpr, n, start, end, 0)
     assert np.array_equal(host(xd), xr)
