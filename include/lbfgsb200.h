@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LBFGSB200_ABI_VERSION 1
+#define LBFGSB200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -49,7 +49,8 @@ enum {
     LBFGSB200_ERR_INVALID_DNORM = -7,       /* ensure!(dnorm.is_sign_positive())  src/lbfgs.rs:544 */
     LBFGSB200_ERR_CUDA = -20,               /* CUDA runtime failure, or no CUDA device */
     LBFGSB200_ERR_NCCL = -21,               /* NCCL failure, or libnccl.so.2 not loadable */
-    LBFGSB200_ERR_STATE = -22               /* call order violated (e.g. propagate before build) */
+    LBFGSB200_ERR_STATE = -22,              /* call order violated (e.g. propagate before build) */
+    LBFGSB200_ERR_UNSUPPORTED = -23         /* the objective has no implementation of the requested entry */
 };
 
 /* line-search algorithms  src/line.rs:39-80 */
@@ -58,6 +59,14 @@ enum {
     LBFGSB200_LS_BACKTRACKING_ARMIJO = 1,
     LBFGSB200_LS_BACKTRACKING_WOLFE = 2,
     LBFGSB200_LS_BACKTRACKING_STRONG_WOLFE = 3
+};
+
+/* reduction order of every dot product / norm / objective sum (param.reduction) */
+enum {
+    LBFGSB200_REDUCE_TREE = 0,        /* production: deterministic two-level tree (warp shuffle, CTA, last-CTA) */
+    LBFGSB200_REDUCE_SEQUENTIAL = 1   /* validation: one thread, the reference's left-to-right fold
+                                         (`iter().sum()`, src/math.rs:40-42): with it a whole solve is
+                                         bit-identical to the reference's CPU arithmetic.  Slow by design. */
 };
 
 /* swallowed line-search errors (src/line.rs:213-220 prints and reverts), report.last_ls_error */
@@ -100,6 +109,7 @@ typedef struct lbfgsb200_param {
     double  max_step_size;          /* 1.0 */
     int64_t damping;                /* 0 */
     int64_t constrain_step_size;    /* 1 (no setter in the reference: src/lbfgs.rs:153,174) */
+    int64_t reduction;              /* LBFGSB200_REDUCE_*; 0 (extension, not in the reference) */
 } lbfgsb200_param_t;
 
 /* Lbfgs::default()  src/lbfgs.rs:156-177, src/line.rs:150-163, src/orthantwise.rs:47-55 */
@@ -112,6 +122,19 @@ void lbfgsb200_param_default(lbfgsb200_param_t *param);
  * memory; the solver sums the partials over ranks).  Must not synchronise.  Non-zero = Err. */
 typedef int (*lbfgsb200_eval_fn)(void *user, const double *x_dev, double *g_dev, int64_t n_local,
                                  void *stream, double *fx_dev);
+
+/* Optional FUSED line-search trial (north_star: "line-search trial points x+alpha*d come from fused
+ * multi-reductions").  One call replaces, for one trial of src/line.rs:283-288 / :741-742,
+ *   take_line_step (src/core.rs:155-164)  x = xp + step*d
+ *   evaluate       (src/core.rs:119-132)  g = grad f(x), f
+ *   dg_unchecked   (src/core.rs:114-116)  g.d          and gnorm / xnorm (src/core.rs:183-194)
+ * by ONE pass that reads xp and d and writes x and g (2R 2W instead of 5R 3W over three kernels):
+ *   out_dev[0] = this rank's partial f(x), out_dev[1] = g.d, out_dev[2] = g.g, out_dev[3] = x.x  (partials)
+ * Element-wise arithmetic must be that of the unfused path (x = xp + step*d without FMA).  Same rules as
+ * lbfgsb200_eval_fn: enqueue on `stream`, do not synchronise, non-zero = Err.  Not used for OWL-QN. */
+typedef int (*lbfgsb200_trial_eval_fn)(void *user, const double *xp_dev, const double *d_dev, double step,
+                                       double *x_dev, double *g_dev, int64_t n_local, void *stream,
+                                       double *out_dev);
 
 /* Progress  src/core.rs:221-250; x/gx are device pointers to this rank's shard */
 typedef struct lbfgsb200_progress {
@@ -172,6 +195,9 @@ const char *lbfgsb200_last_error(const lbfgsb200_solver_t *solver);
 int lbfgsb200_minimize(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user,
                        lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report);
 
+/* Registers (fn != NULL) or clears the fused trial evaluate for the following build()/minimize() calls. */
+int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eval_fn fn, void *user);
+
 /* The iterative API  src/lbfgs.rs:443-566 */
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user);
 /* is_converged (src/lbfgs.rs:489-494): 1 = stop, 0 = continue; *stop_status gets the OK_* reason */
@@ -205,7 +231,8 @@ enum {
     LBFGSB200_K_FORWARD = 8,    /* two-loop forward step                             src/lbfgs.rs:594-601 */
     LBFGSB200_K_EVALUATE = 9,   /* the user's device evaluate */
     LBFGSB200_K_PRIMITIVE = 10, /* unfused LbfgsMath primitives                      src/math.rs:31-82 */
-    LBFGSB200_K_COUNT = 11
+    LBFGSB200_K_TRIAL_EVAL = 11,/* fused trial step + evaluate + dots (lbfgsb200_trial_eval_fn) */
+    LBFGSB200_K_COUNT = 12
 };
 typedef struct lbfgsb200_profile {
     int64_t launches[LBFGSB200_K_COUNT];        /* kernels launched (evaluate: callback invocations) */
@@ -259,9 +286,18 @@ int  lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const do
 /* all-pairs Lennard-Jones  examples/lj.rs:20-64,114-117; n = 3 * atoms */
 int  lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, lbfgsb200_objective_t **out);
 void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective);
+/* LBFGSB200_REDUCE_* for the objective's own sum (f); SEQUENTIAL is implemented for Rosenbrock, Booth and
+ * Lennard-Jones (exp/log in the GLMs are not bit-reproducible against a CPU libm anyway) */
+int  lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int reduction);
 /* the lbfgsb200_eval_fn for every built-in objective: pass the objective handle as `user` */
 int  lbfgsb200_objective_eval(void *objective, const double *x_dev, double *g_dev, int64_t n_local,
                               void *stream, double *fx_dev);
+
+/* the lbfgsb200_trial_eval_fn of the built-in objectives (`user` = the objective handle); implemented for
+ * Rosenbrock, returns LBFGSB200_ERR_UNSUPPORTED for the others.  _has_trial_eval tells without calling. */
+int  lbfgsb200_objective_trial_eval(void *objective, const double *xp_dev, const double *d_dev, double step,
+                                    double *x_dev, double *g_dev, int64_t n_local, void *stream, double *out_dev);
+int  lbfgsb200_objective_has_trial_eval(const lbfgsb200_objective_t *objective);
 
 /* ---- line-search state machines (pure host code; exposed so the scalar logic can be checked
  *      without a GPU)  src/line.rs:226-399, 446-709, 716-784 ----------------------------------- */
@@ -282,6 +318,10 @@ int  lbfgsb200_device_free(void *dev);
 int  lbfgsb200_copy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
 int  lbfgsb200_copy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
 int  lbfgsb200_stream_synchronize(void *stream);
+/* Solver arenas come from the device's default CUDA memory pool and stay cached there after
+ * lbfgsb200_destroy, so repeated solves do not pay the driver's map/unmap of ~(2m+5) n-vectors each time.
+ * This hands the cached pages back to the driver (e.g. before another library needs the HBM). */
+int  lbfgsb200_trim_pool(int device);
 int  lbfgsb200_abi_version(void);
 
 #ifdef __cplusplus

@@ -13,15 +13,17 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lbfgsb200.h")
 
 K_NAMES = ["dots", "owl_pg", "init_dir", "trial", "orthant", "history", "damp", "backward", "forward",
-           "evaluate", "primitive"]
+           "evaluate", "primitive", "trial_eval"]
 K_COUNT = len(K_NAMES)
 
 STATUS_NAMES = {
     0: "OK_CONVERGED", 1: "OK_MAX_ITERATIONS", 2: "OK_MAX_EVALUATIONS", 3: "OK_CANCELLED",
     -1: "ERR_EVALUATE", -2: "ERR_X_NOT_CHANGED", -3: "ERR_G_NOT_CHANGED", -4: "ERR_LINESEARCH",
     -5: "ERR_INVALID_PARAM", -6: "ERR_OWLQN_ZERO_DIRECTION", -7: "ERR_INVALID_DNORM",
-    -20: "ERR_CUDA", -21: "ERR_NCCL", -22: "ERR_STATE",
+    -20: "ERR_CUDA", -21: "ERR_NCCL", -22: "ERR_STATE", -23: "ERR_UNSUPPORTED",
 }
+REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
+ABI_VERSION = 2
 LS_MORETHUENTE, LS_BACKTRACKING_ARMIJO, LS_BACKTRACKING_WOLFE, LS_BACKTRACKING_STRONG_WOLFE = 0, 1, 2, 3
 UNIQUE_ID_BYTES = 128
 
@@ -35,6 +37,7 @@ class Param(C.Structure):
         ("ls_gradient_only", C.c_int64), ("orthantwise", C.c_int64), ("owl_c", C.c_double),
         ("owl_start", C.c_int64), ("owl_end", C.c_int64), ("initial_inverse_hessian", C.c_double),
         ("max_step_size", C.c_double), ("damping", C.c_int64), ("constrain_step_size", C.c_int64),
+        ("reduction", C.c_int64),
     ]
 
 
@@ -61,6 +64,8 @@ class Profile(C.Structure):
 
 
 EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+TRIAL_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
+                            C.c_void_p, C.c_void_p)
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Progress))
 
 _lib = None
@@ -106,6 +111,7 @@ def lib():
     _sig(L, "lbfgsb200_destroy", None, [vp])
     _sig(L, "lbfgsb200_last_error", C.c_char_p, [vp])
     _sig(L, "lbfgsb200_minimize", i32, [vp, vp, vp, vp, vp, vp, pp(Report)])
+    _sig(L, "lbfgsb200_set_trial_evaluate", i32, [vp, vp, vp])
     _sig(L, "lbfgsb200_build", i32, [vp, vp, vp, vp])
     _sig(L, "lbfgsb200_is_converged", i32, [vp, pp(i32)])
     _sig(L, "lbfgsb200_propagate", i32, [vp, pp(Progress)])
@@ -135,6 +141,9 @@ def lib():
     _sig(L, "lbfgsb200_objective_booth", i32, [i32, pp(vp)])
     _sig(L, "lbfgsb200_objective_glm", i32, [i32, i32, vp, vp, i64, i64, pp(vp)])
     _sig(L, "lbfgsb200_objective_lennard_jones", i32, [i32, dbl, dbl, pp(vp)])
+    _sig(L, "lbfgsb200_objective_set_reduction", i32, [vp, i32])
+    _sig(L, "lbfgsb200_objective_has_trial_eval", i32, [vp])
+    _sig(L, "lbfgsb200_objective_trial_eval", i32, [vp, vp, vp, dbl, vp, vp, i64, vp, vp])
     _sig(L, "lbfgsb200_objective_destroy", None, [vp])
     _sig(L, "lbfgsb200_objective_eval", i32, [vp, vp, vp, i64, vp, vp])
     _sig(L, "lbfgsb200_linesearch_begin", vp, [pp(Param), i32, dbl, dbl, dbl])
@@ -148,7 +157,8 @@ def lib():
     _sig(L, "lbfgsb200_copy_h2d", i32, [vp, vp, i64, vp])
     _sig(L, "lbfgsb200_copy_d2h", i32, [vp, vp, i64, vp])
     _sig(L, "lbfgsb200_stream_synchronize", i32, [vp])
-    if L.lbfgsb200_abi_version() != 1:
+    _sig(L, "lbfgsb200_trim_pool", i32, [i32])
+    if L.lbfgsb200_abi_version() != ABI_VERSION:
         raise RuntimeError("liblbfgsb200.so ABI version mismatch; rebuild")
     _lib = L
     return L

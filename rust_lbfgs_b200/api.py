@@ -96,11 +96,15 @@ def _current_stream(device):
 class _Evaluate:
     """Adapts a built-in objective or a Python callable to lbfgsb200_eval_fn."""
 
-    def __init__(self, evaluate, device):
+    def __init__(self, evaluate, device, reduction=0, fused=True):
         self.keep = []
+        self.trial_fn = None
         if hasattr(evaluate, "_eval_ptr"):
             self.fn = evaluate._eval_ptr()
             self.user = evaluate._user_ptr(device)
+            evaluate._set_reduction(device, reduction)
+            if fused:
+                self.trial_fn = evaluate._trial_eval_ptr(device)
             self.keep.append(evaluate)
         elif callable(evaluate):
             import torch
@@ -146,6 +150,7 @@ class Lbfgs:
         self.param = _lib.default_param()
         self._comm = None
         self._shard = None  # (n_global, global_offset)
+        self._fused_trial = True
 
     # -- src/lbfgs.rs:194-383, in source order ------------------------------------------------
     def with_epsilon(self, epsilon):
@@ -236,6 +241,21 @@ class Lbfgs:
         self.param.m = int(m)
         return self
 
+    def with_reduction(self, mode):
+        """"tree" (default): deterministic two-level tree sums.  "sequential": one thread, the reference's
+        left-to-right fold (src/math.rs:40-42) — a whole solve is then bit-identical to the reference's CPU
+        arithmetic; for validation at small n only."""
+        table = {"tree": _lib.REDUCE_TREE, "sequential": _lib.REDUCE_SEQUENTIAL}
+        _require(mode in table, "Invalid reduction mode.")
+        self.param.reduction = table[mode]
+        return self
+
+    def with_fused_trial(self, fused):
+        """Use the objective's fused line-search trial (x = xp + step*d, evaluate and the three dots in one
+        pass) when it has one; default True.  Results are bit-identical either way."""
+        self._fused_trial = bool(fused)
+        return self
+
     def with_shard(self, comm, n_global, global_offset):
         """This rank's x is elements [global_offset, global_offset + len(x)) of an n_global vector;
         `comm` is a rust_lbfgs_b200.dist.Comm (one NCCL rank per GPU)."""
@@ -252,7 +272,8 @@ class Lbfgs:
         ptr, n, device = _ptr_n_device(x)
         solver = _make_solver(self, n, device)
         try:
-            ev = _Evaluate(evaluate, device)
+            ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial)
+            L.lbfgsb200_set_trial_evaluate(solver, ev.trial_fn, ev.user if ev.trial_fn else None)
             cb = None
             cbp = None
             if progress is not None:
@@ -285,7 +306,8 @@ class LbfgsState:
         self._device = device
         self._x_owner = x
         self._solver = _make_solver(builder, n, device)
-        self._ev = _Evaluate(evaluate, device)
+        self._ev = _Evaluate(evaluate, device, builder.param.reduction, builder._fused_trial)
+        self._L.lbfgsb200_set_trial_evaluate(self._solver, self._ev.trial_fn, self._ev.user if self._ev.trial_fn else None)
         st = self._L.lbfgsb200_build(self._solver, ptr, self._ev.fn, self._ev.user)
         if st != 0:
             msg = self._L.lbfgsb200_last_error(self._solver).decode()

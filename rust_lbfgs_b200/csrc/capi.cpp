@@ -95,6 +95,7 @@ void lbfgsb200_param_default(lbfgsb200_param_t *p) {
     p->max_step_size = 1.0;                 // :172
     p->damping = 0;                         // :173
     p->constrain_step_size = 1;             // :174
+    p->reduction = LBFGSB200_REDUCE_TREE;   // extension
 }
 
 // ---- solver ----------------------------------------------------------------------------------
@@ -120,6 +121,11 @@ int lbfgsb200_minimize(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval
                        lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
     return S(solver)->minimize(x_dev, eval, eval_user, progress, progress_user, report);
+}
+int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eval_fn fn, void *user) {
+    if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
+    S(solver)->set_trial_evaluate(fn, user);
+    return 0;
 }
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
@@ -343,6 +349,10 @@ int lbfgsb200_copy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void 
 int lbfgsb200_copy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream) {
     if (cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+int lbfgsb200_trim_pool(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    return lb::trim_pool(device);
 }
 int lbfgsb200_stream_synchronize(void *stream) {
     return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;

@@ -20,6 +20,7 @@ __device__ __forceinline__ double sgn(double v) {  // orthantwise.rs:174-180: 0 
 }
 
 inline int grid_for(const Launch &L, int64_t n, int U) {
+    if (L.sequential) return 1;
     const int64_t nv = n >> 1;
     const int64_t tile = (int64_t)kThreads * U;
     int64_t tiles = (nv + tile - 1) / tile;
@@ -27,6 +28,7 @@ inline int grid_for(const Launch &L, int64_t n, int U) {
     if (tiles > L.max_grid) tiles = L.max_grid;
     return (int)tiles;
 }
+inline int threads_for(const Launch &L) { return L.sequential ? 1 : kThreads; }
 inline void count(const Launch &L) {
     if (L.launch_counter) ++*L.launch_counter;
 }
@@ -110,7 +112,7 @@ struct OwlPgOp {
 template <bool S, bool HAS_D>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_owl_pg(OwlPgOp<S, HAS_D> op, int64_t n, ReduceWs ws, double *out) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    stream_pairs<4, 4>(n, op, acc);
+    stream_pairs<4, HAS_D ? 2 : 4>(n, op, acc);   // three input vectors: U = 4 would not fit 64 registers
     grid_reduce<4>(acc, ws, out);
 }
 
@@ -381,7 +383,7 @@ k_forward(ForwardOp<S, LAST, OWL> op, int64_t n, const double *red_in, double ys
     const double beta = __ldcg(red_in) / ys_j;              // lbfgs.rs:597
     op.coef = __ldcg(alpha_in) - beta;                      // :599
     double acc[3] = {0.0, 0.0, 0.0};
-    stream_pairs<3, 4>(n, op, acc);
+    stream_pairs<3, (LAST && OWL) ? 2 : 4>(n, op, acc);
     grid_reduce<3>(acc, ws, out);
 }
 
@@ -491,34 +493,34 @@ void launch_dots(const Launch &L, const double *g, const double *d, const double
     const int grid = grid_for(L, n, 4);
     count(L);
     if (d) {
-        LB_DISPATCH_S(L, (k_dots<true, true><<<grid, kThreads, 0, L.stream>>>({g, d, x}, n, L.ws, out)),
-                      (k_dots<false, true><<<grid, kThreads, 0, L.stream>>>({g, d, x}, n, L.ws, out)));
+        LB_DISPATCH_S(L, (k_dots<true, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)),
+                      (k_dots<false, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)));
     } else {
-        LB_DISPATCH_S(L, (k_dots<true, false><<<grid, kThreads, 0, L.stream>>>({g, d, x}, n, L.ws, out)),
-                      (k_dots<false, false><<<grid, kThreads, 0, L.stream>>>({g, d, x}, n, L.ws, out)));
+        LB_DISPATCH_S(L, (k_dots<true, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)),
+                      (k_dots<false, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)));
     }
 }
 
 void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g, const double *d, int64_t n,
                    double c, int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, d ? 2 : 4);
     count(L);
     if (d) {
         LB_DISPATCH_S(L,
-                      (k_owl_pg<true, true><<<grid, kThreads, 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
-                      (k_owl_pg<false, true><<<grid, kThreads, 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
+                      (k_owl_pg<true, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
+                      (k_owl_pg<false, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
     } else {
         LB_DISPATCH_S(L,
-                      (k_owl_pg<true, false><<<grid, kThreads, 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
-                      (k_owl_pg<false, false><<<grid, kThreads, 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
+                      (k_owl_pg<true, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
+                      (k_owl_pg<false, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
     }
 }
 
 void launch_init_dir(const Launch &L, double *d, const double *src, int64_t n, double *out) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_init_dir<true><<<grid, kThreads, 0, L.stream>>>({d, src}, n, L.ws, out)),
-                  (k_init_dir<false><<<grid, kThreads, 0, L.stream>>>({d, src}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_init_dir<true><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)),
+                  (k_init_dir<false><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)));
 }
 
 void launch_trial(const Launch &L, double *x, const double *xp, const double *d, double step, int64_t n,
@@ -526,19 +528,19 @@ void launch_trial(const Launch &L, double *x, const double *xp, const double *d,
     const int grid = grid_for(L, n, 4);
     count(L);
     if (wp) {
-        LB_DISPATCH_S(L, (k_trial<true, true><<<grid, kThreads, 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)),
-                      (k_trial<false, true><<<grid, kThreads, 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)));
+        LB_DISPATCH_S(L, (k_trial<true, true><<<grid, threads_for(L), 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)),
+                      (k_trial<false, true><<<grid, threads_for(L), 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)));
     } else {
-        LB_DISPATCH_S(L, (k_trial<true, false><<<grid, kThreads, 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)),
-                      (k_trial<false, false><<<grid, kThreads, 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)));
+        LB_DISPATCH_S(L, (k_trial<true, false><<<grid, threads_for(L), 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)),
+                      (k_trial<false, false><<<grid, threads_for(L), 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)));
     }
 }
 
 void launch_orthant(const Launch &L, signed char *wp, const double *xp, const double *pg, int64_t n) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_orthant<true><<<grid, kThreads, 0, L.stream>>>({wp, xp, pg}, n)),
-                  (k_orthant<false><<<grid, kThreads, 0, L.stream>>>({wp, xp, pg}, n)));
+    LB_DISPATCH_S(L, (k_orthant<true><<<grid, threads_for(L), 0, L.stream>>>({wp, xp, pg}, n)),
+                  (k_orthant<false><<<grid, threads_for(L), 0, L.stream>>>({wp, xp, pg}, n)));
 }
 
 template <bool S>
@@ -546,7 +548,7 @@ static void history_impl(const Launch &L, const double *x, const double *xp, con
                          const double *pg, double *s, double *y, int64_t n, double nstep, bool damping, double *out,
                          int grid) {
 #define LB_HIST(D, O) \
-    k_history<S, D, O><<<grid, kThreads, 0, L.stream>>>({x, xp, g, gp, pg, s, y, nstep}, n, L.ws, out)
+    k_history<S, D, O><<<grid, threads_for(L), 0, L.stream>>>({x, xp, g, gp, pg, s, y, nstep}, n, L.ws, out)
     if (damping && pg) LB_HIST(true, true);
     else if (damping) LB_HIST(true, false);
     else if (pg) LB_HIST(false, true);
@@ -565,8 +567,8 @@ void launch_history(const Launch &L, const double *x, const double *xp, const do
 void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, double omt, double theta) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_damp<true><<<grid, kThreads, 0, L.stream>>>({y, gp, nstep, omt, theta}, n)),
-                  (k_damp<false><<<grid, kThreads, 0, L.stream>>>({y, gp, nstep, omt, theta}, n)));
+    LB_DISPATCH_S(L, (k_damp<true><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)),
+                  (k_damp<false><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)));
 }
 
 template <bool S>
@@ -574,7 +576,7 @@ static void backward_impl(const Launch &L, bool first, bool last, double *q, con
                           const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
                           double *alpha_out, double *out, int grid) {
 #define LB_BWD(F, LA) \
-    k_backward<S, F, LA><<<grid, kThreads, 0, L.stream>>>({q, g, y, s_next, 0.0, gamma}, n, red_in, ys_j, alpha_out, L.ws, out)
+    k_backward<S, F, LA><<<grid, threads_for(L), 0, L.stream>>>({q, g, y, s_next, 0.0, gamma}, n, red_in, ys_j, alpha_out, L.ws, out)
     if (first && last) LB_BWD(true, true);
     else if (first) LB_BWD(true, false);
     else if (last) LB_BWD(false, true);
@@ -596,7 +598,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
                          int64_t n, const double *red_in, double ys_j, const double *alpha_in, int64_t start,
                          int64_t end, int64_t goff, double *out, int grid) {
 #define LB_FWD(LA, OW) \
-    k_forward<S, LA, OW><<<grid, kThreads, 0, L.stream>>>({r, s, aux, 0.0, start, end, goff}, n, red_in, ys_j, alpha_in, L.ws, out)
+    k_forward<S, LA, OW><<<grid, threads_for(L), 0, L.stream>>>({r, s, aux, 0.0, start, end, goff}, n, red_in, ys_j, alpha_in, L.ws, out)
     if (last && owl) LB_FWD(true, true);
     else if (last) LB_FWD(true, false);
     else LB_FWD(false, false);
@@ -606,7 +608,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
 void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
                     const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
                     int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, (last && owl) ? 2 : 4);
     count(L);
     const double *aux = last ? g_or_pg : y_next;
     if (L.streaming) forward_impl<true>(L, last, owl, r, s, aux, n, red_in, ys_j, alpha_in, start, end, goff, out, grid);
@@ -617,16 +619,16 @@ void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t 
                           int64_t goff, double *out) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_owl_constrain<true><<<grid, kThreads, 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)),
-                  (k_owl_constrain<false><<<grid, kThreads, 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_owl_constrain<true><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)),
+                  (k_owl_constrain<false><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)));
 }
 
 template <int KIND>
 static void prim_impl(const Launch &L, double *out, const double *a, const double *b, double c, int64_t n) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_prim<true, KIND><<<grid, kThreads, 0, L.stream>>>({out, a, b, c}, n)),
-                  (k_prim<false, KIND><<<grid, kThreads, 0, L.stream>>>({out, a, b, c}, n)));
+    LB_DISPATCH_S(L, (k_prim<true, KIND><<<grid, threads_for(L), 0, L.stream>>>({out, a, b, c}, n)),
+                  (k_prim<false, KIND><<<grid, threads_for(L), 0, L.stream>>>({out, a, b, c}, n)));
 }
 void launch_vecadd(const Launch &L, double *y, const double *x, double c, int64_t n) { prim_impl<P_ADD>(L, y, x, nullptr, c, n); }
 void launch_vecscale(const Launch &L, double *y, double c, int64_t n) { prim_impl<P_SCALE>(L, y, nullptr, nullptr, c, n); }
@@ -638,8 +640,8 @@ void launch_vecdiff(const Launch &L, double *z, const double *x, const double *y
 void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n, double *out) {
     const int grid = grid_for(L, n, 4);
     count(L);
-    LB_DISPATCH_S(L, (k_dot<true><<<grid, kThreads, 0, L.stream>>>({x, y}, n, L.ws, out)),
-                  (k_dot<false><<<grid, kThreads, 0, L.stream>>>({x, y}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_dot<true><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)),
+                  (k_dot<false><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)));
 }
 
 }  // namespace lb

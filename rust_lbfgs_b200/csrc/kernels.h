@@ -13,6 +13,7 @@ struct Launch {
     cudaStream_t stream = nullptr;
     int max_grid = 148 * 8;   // CTAs: a multiple of the SM count (set from the device at create)
     bool streaming = true;    // evict-first loads/stores (vectors much larger than L2)
+    bool sequential = false;  // reference-order reductions: every kernel runs as <<<1, 1>>> (validation only)
     ReduceWs ws{};            // level-2 reduction workspace
     int64_t *launch_counter = nullptr;
 };

@@ -23,6 +23,7 @@ enum Kind { OBJ_ROSENBROCK = 0, OBJ_BOOTH = 1, OBJ_GLM = 2, OBJ_LJ = 3 };
 
 struct Objective {
     int kind = 0;
+    bool sequential = false;     // LBFGSB200_REDUCE_SEQUENTIAL: f summed in the reference's order by one thread
     DeviceInfo dev{};
     ReduceWs ws{};
     // GLM
@@ -60,6 +61,49 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock(RosenOp<S> 
     double acc[1] = {0.0};
     stream_pairs<1, 4>(n, op, acc);
     grid_reduce<1>(acc, ws, fx);
+}
+
+// Fused line-search trial for Rosenbrock (lbfgsb200_trial_eval_fn): x = xp + step*d, g = grad f(x) and
+// {f, g.d, g.g, x.x} in ONE pass, 2R 2W instead of K1 (2R 1W) + k_rosenbrock (1R 1W) + K2 (3R).  Same
+// per-element arithmetic, same tile shape (U = 4) and grid as those three kernels, so every sum sees the same
+// terms in the same order: the fused and unfused paths give bit-identical scalars.
+template <bool S>
+struct RosenTrialOp {
+    const double *xp, *d;
+    double *x, *g;
+    double step;
+    struct Regs { double2 xp, d; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const {
+        r.xp = ld2<S>(xp, i);
+        r.d = ld2<S>(d, i);
+    }
+    __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[4]) const {
+        double2 xo;
+        xo.x = r.xp.x + step * r.d.x;                       // veccpy + vecadd, core.rs:156-157
+        xo.y = r.xp.y + step * r.d.y;
+        const double x0 = xo.x, x1 = xo.y;
+        const double t1 = 1.0 - x0;                         // lib.rs:85
+        const double t2 = 10.0 * (x1 - x0 * x0);            // :86
+        double2 o;
+        o.y = 20.0 * t2;                                    // :87
+        o.x = -2.0 * (x0 * o.y + t1);                       // :88
+        acc[0] += t1 * t1 + t2 * t2;                        // :89
+        acc[1] += o.x * r.d.x;                              // g.d, core.rs:114-116
+        acc[2] += o.x * o.x;                                // g.g, core.rs:183-190
+        acc[3] += x0 * x0;                                  // x.x, core.rs:192-194
+        acc[1] += o.y * r.d.y;
+        acc[2] += o.y * o.y;
+        acc[3] += x1 * x1;
+        st2<S>(x, i, xo);
+        st2<S>(g, i, o);
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[4]) const {}
+};
+template <bool S>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_trial(RosenTrialOp<S> op, int64_t n, ReduceWs ws, double *out) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    stream_pairs<4, 4>(n, op, acc);
+    grid_reduce<4>(acc, ws, out);
 }
 
 // ---- Booth -----------------------------------------------------------------------------------
@@ -175,19 +219,57 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
     grid_reduce<1>(acc, ws, fx);
 }
 
+// Reference-order energy (LBFGSB200_REDUCE_SEQUENTIAL): one thread walks the pairs (i, j < i) exactly as
+// examples/lj.rs:48-52 does, so the energy is the same left-to-right fold (forces above already are).
+__global__ void k_lj_energy_seq(const double *__restrict__ x, int64_t natoms, double eps, double sigma, double *fx) {
+    double e = 0.0;
+    for (int64_t i = 0; i < natoms; ++i) {
+        for (int64_t j = 0; j < i; ++j) {
+            const double d0 = x[3 * i] - x[3 * j], d1 = x[3 * i + 1] - x[3 * j + 1], d2 = x[3 * i + 2] - x[3 * j + 2];
+            const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const double qq = sigma / r;
+            const double q2 = qq * qq;
+            const double s6 = q2 * (q2 * q2);
+            e += 4.0 * eps * (s6 * s6 - s6);
+        }
+    }
+    *fx = e;
+}
+
+inline int stream_grid(const Objective *o, int64_t n) {
+    if (o->sequential) return 1;
+    const int64_t tile = (int64_t)kThreads * 4;
+    int64_t tiles = ((n >> 1) + tile - 1) / tile;
+    const int64_t cap = (int64_t)o->dev.sm_count * o->dev.blocks_per_sm;
+    if (tiles > cap) tiles = cap;
+    if (tiles < 1) tiles = 1;
+    return (int)tiles;
+}
+
+int trial_impl(Objective *o, const double *xp, const double *d, double step, double *x, double *g, int64_t n,
+               cudaStream_t stream, double *out) {
+    if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
+    if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    const int grid = stream_grid(o, n);
+    const int threads = o->sequential ? 1 : kThreads;
+    // 4 vectors in flight per trial; the same L2 rule as the solver's (working set vs 0.75 L2)
+    const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
+    if (streaming) k_rosenbrock_trial<true><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, o->ws, out);
+    else k_rosenbrock_trial<false><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, o->ws, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
 int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t stream, double *fx) {
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     switch (o->kind) {
         case OBJ_ROSENBROCK: {
             if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;  // the reference indexes x[i+1] (lib.rs:86)
-            const int64_t tile = (int64_t)kThreads * 4;
-            int64_t tiles = ((n >> 1) + tile - 1) / tile;
-            const int64_t cap = (int64_t)o->dev.sm_count * o->dev.blocks_per_sm;
-            if (tiles > cap) tiles = cap;
-            if (tiles < 1) tiles = 1;
+            const int grid = stream_grid(o, n);
+            const int threads = o->sequential ? 1 : kThreads;
             const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
-            if (streaming) k_rosenbrock<true><<<(int)tiles, kThreads, 0, stream>>>({x, g}, n, o->ws, fx);
-            else k_rosenbrock<false><<<(int)tiles, kThreads, 0, stream>>>({x, g}, n, o->ws, fx);
+            if (streaming) k_rosenbrock<true><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);
+            else k_rosenbrock<false><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);
             break;
         }
         case OBJ_BOOTH:
@@ -212,6 +294,7 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
             const int64_t blocks = (na + kLjTile - 1) / kLjTile;
             if (blocks > o->ws.stride) return LBFGSB200_ERR_INVALID_PARAM;
             k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, na, o->eps, o->sigma, o->ws, fx);
+            if (o->sequential) k_lj_energy_seq<<<1, 1, 0, stream>>>(x, na, o->eps, o->sigma, fx);
             break;
         }
         default:
@@ -279,6 +362,23 @@ int lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, 
     o->sigma = sigma;
     *out = reinterpret_cast<lbfgsb200_objective_t *>(o);
     return 0;
+}
+int lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int reduction) {
+    lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
+    if (!o || (reduction != LBFGSB200_REDUCE_TREE && reduction != LBFGSB200_REDUCE_SEQUENTIAL)) return LBFGSB200_ERR_INVALID_PARAM;
+    if (reduction == LBFGSB200_REDUCE_SEQUENTIAL && o->kind == lb::OBJ_GLM) return LBFGSB200_ERR_UNSUPPORTED;
+    o->sequential = reduction == LBFGSB200_REDUCE_SEQUENTIAL;
+    return 0;
+}
+int lbfgsb200_objective_has_trial_eval(const lbfgsb200_objective_t *objective) {
+    const lb::Objective *o = reinterpret_cast<const lb::Objective *>(objective);
+    return (o && o->kind == lb::OBJ_ROSENBROCK) ? 1 : 0;
+}
+int lbfgsb200_objective_trial_eval(void *objective, const double *xp_dev, const double *d_dev, double step,
+                                   double *x_dev, double *g_dev, int64_t n_local, void *stream, double *out_dev) {
+    if (!objective || !xp_dev || !d_dev || !x_dev || !g_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::trial_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, x_dev, g_dev, n_local,
+                          (cudaStream_t)stream, out_dev);
 }
 void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
     lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);

@@ -49,6 +49,11 @@ template <int NACC>
 __device__ __forceinline__ void grid_reduce(double (&acc)[NACC], const ReduceWs &ws, double *__restrict__ out) {
     __shared__ double sm[NACC][kWarps];
     __shared__ bool is_last;
+    if (blockDim.x == 1) {  // reference-order mode (<<<1, 1>>>): acc[] already is the sequential fold
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) out[a] = acc[a];
+        return;
+    }
     block_sum<NACC>(acc, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -99,9 +104,22 @@ __device__ __forceinline__ void st2(double *__restrict__ p, int64_t i, double2 v
 //   op.load(Regs&, int64 pair)    issue the loads
 //   op.apply(Regs&, int64 pair, double (&acc)[NACC])   compute, store, accumulate
 //   op.tail(int64 elem, acc)      scalar path for element n-1 when n is odd
+//
+// Reference-order mode: launched as <<<1, 1>>> the single thread walks the elements in index order, so
+// every accumulator is exactly the sequential left-to-right fold of `vecdot` (src/math.rs:40-42) and a
+// whole solve is bit-identical to the reference's CPU arithmetic (validation only: one thread).
 template <int NACC, int U, class Op>
 __device__ __forceinline__ void stream_pairs(int64_t n, Op &op, double (&acc)[NACC]) {
     const int64_t nv = n >> 1;
+    if (blockDim.x == 1) {
+        for (int64_t i = 0; i < nv; ++i) {
+            typename Op::Regs r;
+            op.load(r, i);
+            op.apply(r, i, acc);
+        }
+        if (n & 1) op.tail(n - 1, acc);
+        return;
+    }
     constexpr int64_t kTile = (int64_t)kThreads * U;
     for (int64_t base = (int64_t)blockIdx.x * kTile; base < nv; base += (int64_t)gridDim.x * kTile) {
         typename Op::Regs r[U];

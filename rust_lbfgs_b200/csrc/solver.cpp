@@ -1,6 +1,7 @@
 // solver.cpp — see solver.h.  Compiled by nvcc as host code with -ffp-contract=off.
 #include "solver.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,10 +47,45 @@ void free_reduce_ws(ReduceWs *ws) {
     ws->ticket = nullptr;
 }
 
+// The arena (2m + 4..5 n-vectors: 12.8 GB at n = 1e8, m = 6) comes from the device's default CUDA memory pool
+// with the release threshold lifted, so a process that solves repeatedly pays the driver's map/unmap of
+// those pages once (measured on B200: cudaMalloc + cudaFree of the arena cost 30 ms .. 1.3 s per solve,
+// against ~9 ms per L-BFGS iteration).  lbfgsb200_trim_pool() hands the cached pages back.
+// LBFGSB200_POOL=0 falls back to cudaMalloc / cudaFree.
+static bool use_pool(int device) {
+    static int cached[64];  // 0 = unknown, 1 = pool, 2 = plain
+    if (device < 0 || device >= 64) return false;
+    if (cached[device] == 0) {
+        int ok = 0;
+        cudaMemPool_t pool = nullptr;
+        if (env_int("LBFGSB200_POOL", 1) != 0 &&
+            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && ok &&
+            cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+        } else {
+            ok = 0;
+        }
+        cudaGetLastError();
+        cached[device] = ok ? 1 : 2;
+    }
+    return cached[device] == 1;
+}
+
+int trim_pool(int device) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
 Solver::~Solver() {
     for (auto &p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
     for (auto e : event_pool_) cudaEventDestroy(e);
-    if (arena_) cudaFree(arena_);
+    if (arena_) {
+        if (arena_pooled_) cudaFreeAsync(arena_, stream_);
+        else cudaFree(arena_);
+    }
     if (scal_dev_) cudaFree(scal_dev_);
     if (scal_host_) cudaFreeHost(scal_host_);
     free_reduce_ws(&ws_);
@@ -81,6 +117,10 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     if (!(p.ls_min_step >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter min_step specified.");
     if (!(p.delta >= 0.0)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter delta specified.");
     if (p.ls_algorithm < 0 || p.ls_algorithm > 3) return fail(LBFGSB200_ERR_INVALID_PARAM, "unknown line search algorithm");
+    if (p.reduction != LBFGSB200_REDUCE_TREE && p.reduction != LBFGSB200_REDUCE_SEQUENTIAL)
+        return fail(LBFGSB200_ERR_INVALID_PARAM, "unknown reduction mode");
+    if (p.reduction == LBFGSB200_REDUCE_SEQUENTIAL && comm && comm_size(comm) > 1)
+        return fail(LBFGSB200_ERR_INVALID_PARAM, "sequential (reference-order) reductions are single-GPU only");
 
     p_ = p;
     m_ = p.m;
@@ -90,6 +130,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     comm_ = comm;
     stream_ = stream;
     owl_ = p.orthantwise != 0;
+    sequential_ = p.reduction == LBFGSB200_REDUCE_SEQUENTIAL;
     if (owl_) {
         if (std::signbit(p.owl_c)) return fail(LBFGSB200_ERR_INVALID_PARAM, "Invalid parameter orthantwise c parameter specified.");
         owl_start_ = p.owl_start;                                       // Orthantwise::start_end, orthantwise.rs:59-67
@@ -114,8 +155,10 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     const int64_t vec_bytes = round_up(n_ * (int64_t)sizeof(double), kAlign);
     const int64_t nvec = 4 + (owl_ ? 1 : 0) + 2 * m_;
     const int64_t wp_bytes = owl_ ? round_up(n_, kAlign) : 0;
-    e = cudaMalloc(&arena_, (size_t)(nvec * vec_bytes + wp_bytes));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(arena)");
+    arena_pooled_ = use_pool(device);
+    if (arena_pooled_) e = cudaMallocAsync(&arena_, (size_t)(nvec * vec_bytes + wp_bytes), stream_);
+    else e = cudaMalloc(&arena_, (size_t)(nvec * vec_bytes + wp_bytes));
+    if (e != cudaSuccess) { arena_ = nullptr; return cuda_fail(e, "cudaMalloc(arena)"); }
     char *base = (char *)arena_;
     auto take = [&]() { double *r = (double *)base; base += vec_bytes; return r; };
     xbuf_[1] = take();
@@ -155,6 +198,7 @@ Launch Solver::launch_cfg() {
     L.stream = stream_;
     L.max_grid = dev_.sm_count * dev_.blocks_per_sm;
     L.streaming = streaming_;
+    L.sequential = sequential_;
     L.ws = ws_;
     L.launch_counter = &launch_counter_;
     return L;
@@ -242,6 +286,13 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
         launch_dots(L, g, want_gd ? d_or_null : nullptr, x, n_, sl + 1);
         prof_end(LBFGSB200_K_DOTS, (want_gd ? 3.0 : 2.0) * vbytes);
     }
+    return finish_eval(erc, false, dg_out);
+}
+
+// The scalar half of an evaluation: (optional) cross-rank sum, D2H of the slot, the one host sync per trial.
+bool Solver::finish_eval(int erc, bool fused, double *dg_out) {
+    double *sl = slot(SLOT_EVAL);
+    const bool multi = comm_ && comm_size(comm_) > 1;
     if (multi) {  // an Err on any rank must be seen by every rank (replicated control flow)
         const double flag = erc != 0 ? 1.0 : 0.0;
         scal_host_[kMaxAcc] = flag;
@@ -252,7 +303,7 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
     if (multi && h[7] != 0.0) return false;
 
     neval_ += 1;
-    if (owl_) {
+    if (owl_ && !fused) {
         fx_ = h[0];
         fx_ += h[1];        // fx += x1norm, core.rs:123-124
         gg_ = h[2];
@@ -265,6 +316,27 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
         xx_ = h[3];
     }
     return true;
+}
+
+// One line-search trial: take_line_step (core.rs:155-164) + evaluate (:119-132) + dg (:114-116).
+// With a fused trial evaluate registered (and no OWL-QN) this is ONE pass over xp and d.
+bool Solver::trial_point(const double *xp, double stp, double *dg_out) {
+    const double vbytes = 8.0 * (double)n_;
+    double *x = xbuf_[cur_x_];
+    if (trial_eval_ && !owl_) {
+        prof_begin(LBFGSB200_K_TRIAL_EVAL);
+        const int erc = trial_eval_(trial_user_, xp, d_, stp, x, gbuf_[cur_g_], n_, (void *)stream_, slot(SLOT_EVAL));
+        prof_end(LBFGSB200_K_TRIAL_EVAL, 4.0 * vbytes);
+        launch_counter_ += 1;
+        const bool multi = comm_ && comm_size(comm_) > 1;
+        if (erc != 0 && !multi) return false;
+        return finish_eval(erc, true, dg_out);
+    }
+    Launch L = launch_cfg();
+    prof_begin(LBFGSB200_K_TRIAL);
+    launch_trial(L, x, xp, d_, stp, n_, owl_ ? wp_ : nullptr, owl_start_, owl_end_, goff_);
+    prof_end(LBFGSB200_K_TRIAL, 3.0 * vbytes + (owl_ ? (double)n_ : 0.0));
+    return evaluate_point(d_, dg_out);
 }
 
 void Solver::fill_progress(lbfgsb200_progress_t *out, double step_value) const {  // core.rs:253-268
@@ -373,11 +445,8 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     }
     double stp = 0.0;
     while (ls.next_trial(&stp)) {
-        prof_begin(LBFGSB200_K_TRIAL);  // take_line_step, core.rs:155-164
-        launch_trial(L, x, xp, d_, stp, n_, owl_ ? wp_ : nullptr, owl_start_, owl_end_, goff_);
-        prof_end(LBFGSB200_K_TRIAL, 3.0 * vbytes + (owl_ ? (double)n_ : 0.0));
         double dg = 0.0;
-        const bool ok = evaluate_point(d_, &dg);
+        const bool ok = trial_point(xp, stp, &dg);
         if (!ok && last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;  // CUDA / NCCL failure is fatal
         ls.feed(ok, fx_, dg);
     }
@@ -505,7 +574,14 @@ int Solver::finish() {
 // ---- Lbfgs::minimize, src/lbfgs.rs:399-421 -----------------------------------------------------
 int Solver::minimize(double *x_dev, lbfgsb200_eval_fn eval, void *user, lbfgsb200_progress_fn prog, void *prog_user,
                      lbfgsb200_report_t *rep) {
+    const bool dbg = env_int("LBFGSB200_DEBUG_TIMING", 0) != 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    auto t0 = now();
     int rc = build(x_dev, eval, user);
+    if (dbg) fprintf(stderr, "[lbfgsb200] build %.3f ms\n", ms(t0, now()));
     if (rc != 0) {
         report(rep);
         return rc;
@@ -515,7 +591,9 @@ int Solver::minimize(double *x_dev, lbfgsb200_eval_fn eval, void *user, lbfgsb20
         int st = 0;
         if (is_converged(&st)) { status = st; break; }
         lbfgsb200_progress_t pr;
+        auto t1 = now();
         rc = propagate(&pr);
+        if (dbg) fprintf(stderr, "[lbfgsb200] propagate k=%lld ncall=%lld %.3f ms\n", (long long)k_, (long long)ncall_, ms(t1, now()));
         if (rc != 0) { status = rc; break; }
         if (prog && prog(prog_user, &pr) != 0) { status = LBFGSB200_OK_CANCELLED; break; }
     }

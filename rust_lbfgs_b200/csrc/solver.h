@@ -34,6 +34,8 @@ struct DeviceInfo {
     int blocks_per_sm = 4;
 };
 int query_device(int device, DeviceInfo *out);
+// returns the pages cached by the solver arenas' memory pool to the driver
+int trim_pool(int device);
 // allocates the level-2 reduction workspace for `info`
 int alloc_reduce_ws(const DeviceInfo &info, ReduceWs *ws);
 void free_reduce_ws(ReduceWs *ws);
@@ -58,6 +60,9 @@ class Solver {
     const double *direction() const { return d_; }
     const std::string &error() const { return err_; }
 
+    // optional fused trial evaluate (lbfgsb200_trial_eval_fn); ignored for OWL-QN
+    void set_trial_evaluate(lbfgsb200_trial_eval_fn fn, void *user) { trial_eval_ = fn; trial_user_ = user; }
+
     void profile_enable(bool timing) { timing_ = timing; }
     void profile_get(lbfgsb200_profile_t *out);
     void profile_reset();
@@ -70,6 +75,8 @@ class Solver {
     int fail(int status, const char *msg);
     int cuda_fail(cudaError_t e, const char *what);
     bool evaluate_point(const double *d_or_null, double *dg_out);  // evaluate + K2/K3 + allreduce + sync
+    bool trial_point(const double *xp, double stp, double *dg_out); // K1 + evaluate_point, or the fused callback
+    bool finish_eval(int erc, bool fused, double *dg_out);         // allreduce + D2H + sync of SLOT_EVAL
     int fetch(int s, int count, double *host);                     // allreduce + D2H + sync of a slot
     int reduce_across_ranks(int s, int count);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
@@ -91,9 +98,11 @@ class Solver {
     cudaStream_t stream_ = nullptr;
     Comm *comm_ = nullptr;
     bool streaming_ = true;
+    bool sequential_ = false;     // param.reduction == LBFGSB200_REDUCE_SEQUENTIAL
 
     // HBM
     void *arena_ = nullptr;
+    bool arena_pooled_ = false;             // cudaMallocAsync from the device's default pool
     double *xbuf_[2] = {nullptr, nullptr};  // [0] = caller's x, [1] = ours
     double *gbuf_[2] = {nullptr, nullptr};
     double *d_ = nullptr, *pg_ = nullptr;
@@ -108,6 +117,8 @@ class Solver {
     // host scalars
     lbfgsb200_eval_fn eval_ = nullptr;
     void *eval_user_ = nullptr;
+    lbfgsb200_trial_eval_fn trial_eval_ = nullptr;
+    void *trial_user_ = nullptr;
     bool built_ = false;
     double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point
     double dginit_ = 0.0;                      // g.d (pg.d) for the next line search

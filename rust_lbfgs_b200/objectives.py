@@ -18,6 +18,18 @@ class _Builtin:
     def _eval_ptr(self):
         return C.cast(_lib.lib().lbfgsb200_objective_eval, C.c_void_p)
 
+    def _trial_eval_ptr(self, device):
+        """The lbfgsb200_trial_eval_fn of this objective (fused trial step + evaluate + dots), or None."""
+        L = _lib.lib()
+        if L.lbfgsb200_objective_has_trial_eval(self._user_ptr(device)) != 1:
+            return None
+        return C.cast(L.lbfgsb200_objective_trial_eval, C.c_void_p)
+
+    def _set_reduction(self, device, reduction):
+        st = _lib.lib().lbfgsb200_objective_set_reduction(self._user_ptr(device), reduction)
+        if st != 0:
+            raise ValueError(f"objective does not support reduction mode {reduction}: {_lib.STATUS_NAMES.get(st, st)}")
+
     def _user_ptr(self, device):
         if device not in self._handles:
             L = _lib.lib()

@@ -51,10 +51,11 @@ def test_param_defaults_match_reference():
 
 
 def test_param_layout_matches_oracle_order(oracle):
-    """The product POD is the oracle POD with struct_size in front and without reduction_mode."""
+    """The product POD is the oracle POD with struct_size in front; both end with their own (different)
+    reduction selector: the product's tree / reference-order, the oracle's sequential / compensated."""
     a = [f[0] for f in _lib.Param._fields_][1:]
-    b = [f[0] for f in oracle.Param._fields_][:-1]
-    assert a == b
+    b = [f[0] for f in oracle.Param._fields_]
+    assert a[:-1] == b[:-1] and a[-1] == "reduction" and b[-1] == "reduction_mode"
 
 
 def test_builder_mirrors_reference_setters():
@@ -75,6 +76,8 @@ def test_builder_mirrors_reference_setters():
     assert (g.ls_gradient_only, g.damping, g.ls_algorithm) == (1, 1, _lib.LS_BACKTRACKING_STRONG_WOLFE)
     assert R.lbfgs().with_orthantwise(1.0, 0).param.owl_end == -1
     assert R.lbfgs().with_m(20).param.m == 20
+    assert R.default_param().reduction == _lib.REDUCE_TREE
+    assert R.lbfgs().with_reduction("sequential").param.reduction == _lib.REDUCE_SEQUENTIAL
     for bad in (lambda: R.lbfgs().with_epsilon(-1.0), lambda: R.lbfgs().with_max_step_size(-0.0),
                 lambda: R.lbfgs().with_linesearch_gtol(1.5), lambda: R.lbfgs().with_linesearch_gtol(1e-5),
                 lambda: R.lbfgs().with_orthantwise(-1.0, 0), lambda: R.lbfgs().with_linesearch_ftol(-1.0),

@@ -1,0 +1,195 @@
+"""BIT-EXACT parity of whole solves against the faithful oracle (the reference's CPU arithmetic).
+
+The production kernels sum with a deterministic two-level tree; the reference sums left to right
+(`iter().sum()`, src/math.rs:40-42).  L-BFGS amplifies those last-bit differences, which is why
+tests/test_gpu_solver.py needs tolerances.  With `with_reduction("sequential")` the SAME kernels run as
+<<<1, 1>>> and every accumulator becomes the reference's sequential fold; element-wise arithmetic is already
+bit-identical (-fmad=false, the reference's operation order) and the scalar control code is host f64
+without contraction.  So every iterate must then equal the oracle's BIT FOR BIT: x, gx, fx, ||x||, ||g||,
+step, the evaluation counts and the termination status — for every line search, OWL-QN, damping,
+gradient-only, history depth and stop condition.  What remains different in production is the summation
+order alone.
+
+Also here: the fused line-search trial (one pass: x = xp + step*d, gradient, f, g.d, g.g, x.x) must give the
+same bits as the three unfused kernels, in both reduction modes."""
+import os
+
+import numpy as np
+import pytest
+
+import rust_lbfgs_b200 as R
+from gpu_util import gpu_minimize
+from util import rosenbrock_x0
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_run(oracle, x0, name, **kw):
+    return oracle.minimize(oracle.default_param(**kw), np.asarray(x0, dtype=np.float64).copy(),
+                           oracle.Objective.builtin(name), record_x=True)
+
+
+def assert_bit_identical(ref, got, what=""):
+    assert got["status_name"] == ref["status_name"], (what, got["status_name"], ref["status_name"], got.get("error"))
+    assert len(got["trace"]) == len(ref["trace"]), (what, len(got["trace"]), len(ref["trace"]))
+    for i, (a, b) in enumerate(zip(ref["trace"], got["trace"])):
+        for key in ("niter", "neval", "ncall"):
+            assert a[key] == b[key], (what, i + 1, key, a[key], b[key])
+        for key in ("fx", "xnorm", "gnorm", "step"):
+            assert a[key] == b[key] or (np.isnan(a[key]) and np.isnan(b[key])), (what, i + 1, key, a[key], b[key])
+        assert np.array_equal(a["x"], b["x"]), (what, i + 1, "x", float(np.max(np.abs(a["x"] - b["x"]))))
+        assert np.array_equal(a["gx"], b["gx"]), (what, i + 1, "gx")
+    assert np.array_equal(ref["x"], got["x"]), (what, "final x")
+    rep = got["report"]
+    assert rep.fx == ref["report"]["fx"] and rep.neval == ref["report"]["neval"], what
+    assert rep.xnorm == ref["report"]["xnorm"] and rep.gnorm == ref["report"]["gnorm"], what
+
+
+def seq():
+    return R.lbfgs().with_reduction("sequential")
+
+
+# ---- P2 / P3 / P4 of the reference's own tests, bit for bit ---------------------------------------------------------
+def test_p2_p3_rosenbrock_then_owlqn_bit_exact(oracle):
+    ref = oracle_run(oracle, rosenbrock_x0(100), "rosenbrock")                         # tests/simple.rs:17-40
+    got = gpu_minimize(seq(), rosenbrock_x0(100), R.Rosenbrock())
+    assert_bit_identical(ref, got, "P2")
+    assert len(got["trace"]) == 35 and got["report"].neval == 40
+    ref2 = oracle_run(oracle, ref["x"], "rosenbrock", orthantwise=1, owl_c=1.0, owl_start=0, owl_end=99)
+    got2 = gpu_minimize(seq().with_orthantwise(1.0, 0, 99), got["x"], R.Rosenbrock())  # tests/simple.rs:43-54
+    assert_bit_identical(ref2, got2, "P3")
+    assert len(got2["trace"]) == 150 and got2["report"].neval == 338
+    for a, b in zip(ref2["trace"], got2["trace"]):                                     # orthant sign patterns
+        assert np.array_equal(np.sign(a["x"]), np.sign(b["x"]))
+
+
+def test_p4_booth_bit_exact(oracle):
+    ref = oracle_run(oracle, [-1.2, 1.0], "booth")                                     # tests/simple.rs:57-83
+    got = gpu_minimize(seq(), [-1.2, 1.0], R.Booth())
+    assert_bit_identical(ref, got, "P4")
+
+
+# ---- every line search, including the chaotic Armijo run where two CPU summation orders diverge ---------------------
+@pytest.mark.parametrize("algo,name", [(0, "MoreThuente"), (1, "BacktrackingArmijo"), (2, "BacktrackingWolfe"),
+                                       (3, "BacktrackingStrongWolfe")])
+def test_linesearch_algorithms_bit_exact(oracle, algo, name):
+    ref = oracle_run(oracle, rosenbrock_x0(100), "rosenbrock", ls_algorithm=algo)
+    got = gpu_minimize(seq().with_linesearch_algorithm(name), rosenbrock_x0(100), R.Rosenbrock())
+    assert_bit_identical(ref, got, name)
+
+
+@pytest.mark.parametrize("n", [2, 10, 1000, 4098])
+def test_rosenbrock_sizes_bit_exact(oracle, n):
+    ref = oracle_run(oracle, rosenbrock_x0(n), "rosenbrock")
+    got = gpu_minimize(seq(), rosenbrock_x0(n), R.Rosenbrock())
+    assert_bit_identical(ref, got, f"n={n}")
+
+
+def test_options_bit_exact(oracle):
+    """History depth (ring wrap-around at m = 1, 3), stop conditions, step-size options, gtol, OWL-QN ranges."""
+    for kw, b in ((dict(m=1), seq().with_m(1)), (dict(m=3), seq().with_m(3)), (dict(m=20), seq().with_m(20)),
+                  (dict(max_iterations=10), seq().with_max_iterations(10)),
+                  (dict(max_evaluations=17), seq().with_max_evaluations(17)),
+                  (dict(epsilon=1e-2), seq().with_epsilon(1e-2)),
+                  (dict(max_step_size=0.1), seq().with_max_step_size(0.1)),
+                  (dict(initial_inverse_hessian=0.01), seq().with_initial_step_size(0.01)),
+                  (dict(ls_gtol=0.1), seq().with_linesearch_gtol(0.1)),
+                  (dict(ls_max_linesearch=2), seq().with_max_linesearch(2)),
+                  (dict(orthantwise=1, owl_c=0.3, owl_start=10, owl_end=60), seq().with_orthantwise(0.3, 10, 60)),
+                  (dict(orthantwise=1, owl_c=2.0, owl_start=1, owl_end=-1), seq().with_orthantwise(2.0, 1))):
+        ref = oracle_run(oracle, rosenbrock_x0(100), "rosenbrock", **kw)
+        got = gpu_minimize(b, rosenbrock_x0(100), R.Rosenbrock())
+        assert_bit_identical(ref, got, str(kw))
+
+
+def test_damping_bit_exact(oracle):
+    """Powell damping (src/lbfgs.rs:664-689): case 1 rewrites y, case 2 leaves it."""
+    x0 = rosenbrock_x0(50) * np.linspace(0.5, 1.5, 50)
+    for algo, name in ((1, "BacktrackingArmijo"), (3, "BacktrackingStrongWolfe")):
+        ref = oracle_run(oracle, x0, "rosenbrock", ls_algorithm=algo, damping=1, max_iterations=60)
+        got = gpu_minimize(seq().with_linesearch_algorithm(name).with_damping(True).with_max_iterations(60), x0,
+                           R.Rosenbrock())
+        assert_bit_identical(ref, got, f"damping {name}")
+
+
+def test_lj38_bit_exact(oracle, golden_dir):
+    """examples/lj.rs (LJ38): defaults, damping, gradient-only, and quirk 12's `line search disabled`.
+    sqrt and division are IEEE-exact on both sides, so the all-pairs objective is bit-reproducible too."""
+    p0 = np.load(os.path.join(golden_dir, "lj38.npy")).ravel()
+    for kw, b in ((dict(), seq()),
+                  (dict(damping=1), seq().with_damping(True)),
+                  (dict(ls_gradient_only=1, damping=1, ls_algorithm=3), seq().with_gradient_only()),
+                  (dict(ls_gradient_only=1, damping=1, ls_algorithm=3, ls_max_linesearch=2),
+                   seq().with_gradient_only().with_max_linesearch(2))):
+        ref = oracle_run(oracle, p0, "lj", max_iterations=80, **kw)
+        got = gpu_minimize(b.with_max_iterations(80), p0, R.LennardJones())
+        assert_bit_identical(ref, got, f"lj38 {kw}")
+
+
+def test_error_status_bit_exact(oracle):
+    """Failure paths end with the same status after the same number of iterations (src/line.rs:213-220)."""
+    for kw, b in ((dict(ls_max_linesearch=1), seq().with_max_linesearch(1)),
+                  (dict(ls_min_step=1e-3, ls_algorithm=1), seq().with_linesearch_min_step(1e-3)
+                   .with_linesearch_algorithm("BacktrackingArmijo"))):
+        ref = oracle_run(oracle, rosenbrock_x0(100), "rosenbrock", **kw)
+        got = gpu_minimize(b, rosenbrock_x0(100), R.Rosenbrock())
+        assert got["status_name"] == ref["status_name"], (kw, got["status_name"], ref["status_name"])
+        assert len(got["trace"]) == len(ref["trace"])
+        for a, c in zip(ref["trace"], got["trace"]):
+            assert np.array_equal(a["x"], c["x"]) and a["fx"] == c["fx"] and a["ncall"] == c["ncall"]
+
+
+# ---- fused trial == unfused trial, bit for bit -----------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 100, 2050, 1 << 20, (1 << 22) + 2])
+def test_fused_trial_matches_unfused_bitwise(n):
+    """lbfgsb200_trial_eval_fn (one pass) vs K1 + evaluate + K2 (three passes): same tiles, same trees."""
+    iters = 40 if n <= (1 << 20) else 12
+    a = gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(True), rosenbrock_x0(n), R.Rosenbrock(),
+                     record_x=n <= 4096)
+    b = gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(False), rosenbrock_x0(n), R.Rosenbrock(),
+                     record_x=n <= 4096)
+    assert a["status_name"] == b["status_name"] and len(a["trace"]) == len(b["trace"]) > 3
+    for s, t in zip(a["trace"], b["trace"]):
+        for key in ("neval", "ncall", "fx", "xnorm", "gnorm", "step"):
+            assert s[key] == t[key], (n, s["niter"], key, s[key], t[key])
+        if "x" in s:
+            assert np.array_equal(s["x"], t["x"]) and np.array_equal(s["gx"], t["gx"])
+    assert np.array_equal(a["x"], b["x"])
+
+
+def test_fused_trial_sequential_bit_exact(oracle):
+    ref = oracle_run(oracle, rosenbrock_x0(1000), "rosenbrock")
+    for fused in (True, False):
+        got = gpu_minimize(seq().with_fused_trial(fused), rosenbrock_x0(1000), R.Rosenbrock())
+        assert_bit_identical(ref, got, f"fused={fused}")
+
+
+def test_fused_trial_kernel_direct(oracle):
+    """The C entry lbfgsb200_objective_trial_eval on its own: x and g bit-exact, sums within 1e-13."""
+    import ctypes as C
+    import torch
+    from gpu_util import ck, dev, host, stream
+    L = R.lib()
+    rng = np.random.default_rng(11)
+    for n in (2, 6, 1026, 300000):
+        xp, d = rng.standard_normal(n), rng.standard_normal(n)
+        step = 0.37
+        xr = xp.copy()
+        oracle.lib().oracle_vecadd(xr, d, step, n)
+        gr = np.zeros(n)
+        err = C.c_int(0)
+        fr = oracle.lib().oracle_eval_rosenbrock(None, xr.ctypes.data, gr.ctypes.data, n, C.byref(err))
+        obj = R.Rosenbrock()
+        xpd, dd = dev(xp), dev(d)
+        xd, gd = torch.empty(n, dtype=torch.float64, device="cuda:0"), torch.empty(n, dtype=torch.float64, device="cuda:0")
+        out = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+        ck(L.lbfgsb200_objective_trial_eval(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), step, xd.data_ptr(),
+                                            gd.data_ptr(), n, stream(), out.data_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(host(xd), xr) and np.array_equal(host(gd), gr)
+        o = host(out)
+        for got, want in ((o[0], fr), (o[1], float(gr @ d)), (o[2], float(gr @ gr)), (o[3], float(xr @ xr))):
+            assert abs(got - want) <= 1e-13 * max(abs(want), float(np.abs(gr).max() * np.abs(d).max())), (n, got, want)
+    lj = R.LennardJones()
+    assert L.lbfgsb200_objective_has_trial_eval(lj._user_ptr(0)) == 0
+    assert L.lbfgsb200_objective_has_trial_eval(obj._user_ptr(0)) == 1
