@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblbfgsb200.so")
+# LBFGSB200_SO selects another build of the same library (tuning experiments: scripts/build_variants.sh)
+SO_PATH = os.environ.get("LBFGSB200_SO") or os.path.join(_HERE, "liblbfgsb200.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lbfgsb200.h")
 

@@ -60,7 +60,7 @@ struct DotsOp {
 template <bool S, bool HAS_D>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_dots(DotsOp<S, HAS_D> op, int64_t n, ReduceWs ws, double *out) {
     double acc[3] = {0.0, 0.0, 0.0};
-    stream_pairs<3, 4>(n, op, acc);
+    stream_pairs<3, kUt>(n, op, acc);   // kUt: same element -> thread map as the fused trial kernel
     grid_reduce<3>(acc, ws, out);
 }
 
@@ -112,7 +112,7 @@ struct OwlPgOp {
 template <bool S, bool HAS_D>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_owl_pg(OwlPgOp<S, HAS_D> op, int64_t n, ReduceWs ws, double *out) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    stream_pairs<4, HAS_D ? 2 : 4>(n, op, acc);   // three input vectors: U = 4 would not fit 64 registers
+    stream_pairs<4, HAS_D ? 2 : kU>(n, op, acc);   // three input vectors: U = 4 would not fit 64 registers
     grid_reduce<4>(acc, ws, out);
 }
 
@@ -141,7 +141,7 @@ struct InitDirOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_init_dir(InitDirOp<S> op, int64_t n, ReduceWs ws, double *out) {
     double acc[2] = {0.0, 0.0};
-    stream_pairs<2, 4>(n, op, acc);
+    stream_pairs<2, kU>(n, op, acc);
     grid_reduce<2>(acc, ws, out);
 }
 
@@ -181,7 +181,7 @@ struct TrialOp {
 template <bool S, bool OWL>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_trial(TrialOp<S, OWL> op, int64_t n) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,7 +209,7 @@ struct OrthantOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_orthant(OrthantOp<S> op, int64_t n) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,7 +255,7 @@ template <bool S, bool DAMP, bool OWL>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_history(HistoryOp<S, DAMP, OWL> op, int64_t n, ReduceWs ws, double *out) {
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    stream_pairs<5, 2>(n, op, acc);
+    stream_pairs<5, kUh>(n, op, acc);
     grid_reduce<5>(acc, ws, out);
 }
 
@@ -287,7 +287,7 @@ struct DampOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_damp(DampOp<S> op, int64_t n) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,7 +334,7 @@ k_backward(BackwardOp<S, FIRST, LAST> op, int64_t n, const double *red_in, doubl
     if (blockIdx.x == 0 && threadIdx.x == 0) *alpha_out = alpha;
     op.nalpha = -alpha;
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
     grid_reduce<1>(acc, ws, out);
 }
 
@@ -383,7 +383,7 @@ k_forward(ForwardOp<S, LAST, OWL> op, int64_t n, const double *red_in, double ys
     const double beta = __ldcg(red_in) / ys_j;              // lbfgs.rs:597
     op.coef = __ldcg(alpha_in) - beta;                      // :599
     double acc[3] = {0.0, 0.0, 0.0};
-    stream_pairs<3, (LAST && OWL) ? 2 : 4>(n, op, acc);
+    stream_pairs<3, (LAST && OWL) ? 2 : kU>(n, op, acc);
     grid_reduce<3>(acc, ws, out);
 }
 
@@ -416,7 +416,7 @@ struct OwlConstrainOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_owl_constrain(OwlConstrainOp<S> op, int64_t n, ReduceWs ws, double *out) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
     grid_reduce<1>(acc, ws, out);
 }
 
@@ -456,7 +456,7 @@ struct PrimOp {
 template <bool S, int KIND>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_prim(PrimOp<S, KIND> op, int64_t n) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
 }
 
 template <bool S>
@@ -476,7 +476,7 @@ struct DotOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_dot(DotOp<S> op, int64_t n, ReduceWs ws, double *out) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kU>(n, op, acc);
     grid_reduce<1>(acc, ws, out);
 }
 
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_dot(DotOp<S> op, int64
     } while (0)
 
 void launch_dots(const Launch &L, const double *g, const double *d, const double *x, int64_t n, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kUt);
     count(L);
     if (d) {
         LB_DISPATCH_S(L, (k_dots<true, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)),
@@ -503,7 +503,7 @@ void launch_dots(const Launch &L, const double *g, const double *d, const double
 
 void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g, const double *d, int64_t n,
                    double c, int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, d ? 2 : 4);
+    const int grid = grid_for(L, n, d ? 2 : kU);
     count(L);
     if (d) {
         LB_DISPATCH_S(L,
@@ -517,7 +517,7 @@ void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g
 }
 
 void launch_init_dir(const Launch &L, double *d, const double *src, int64_t n, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_init_dir<true><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)),
                   (k_init_dir<false><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)));
@@ -525,7 +525,7 @@ void launch_init_dir(const Launch &L, double *d, const double *src, int64_t n, d
 
 void launch_trial(const Launch &L, double *x, const double *xp, const double *d, double step, int64_t n,
                   const signed char *wp, int64_t start, int64_t end, int64_t goff) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     if (wp) {
         LB_DISPATCH_S(L, (k_trial<true, true><<<grid, threads_for(L), 0, L.stream>>>({x, xp, d, wp, step, start, end, goff}, n)),
@@ -537,7 +537,7 @@ void launch_trial(const Launch &L, double *x, const double *xp, const double *d,
 }
 
 void launch_orthant(const Launch &L, signed char *wp, const double *xp, const double *pg, int64_t n) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_orthant<true><<<grid, threads_for(L), 0, L.stream>>>({wp, xp, pg}, n)),
                   (k_orthant<false><<<grid, threads_for(L), 0, L.stream>>>({wp, xp, pg}, n)));
@@ -558,14 +558,14 @@ static void history_impl(const Launch &L, const double *x, const double *xp, con
 
 void launch_history(const Launch &L, const double *x, const double *xp, const double *g, const double *gp,
                     const double *pg, double *s, double *y, int64_t n, double nstep, bool damping, double *out) {
-    const int grid = grid_for(L, n, 2);
+    const int grid = grid_for(L, n, kUh);
     count(L);
     if (L.streaming) history_impl<true>(L, x, xp, g, gp, pg, s, y, n, nstep, damping, out, grid);
     else history_impl<false>(L, x, xp, g, gp, pg, s, y, n, nstep, damping, out, grid);
 }
 
 void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, double omt, double theta) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_damp<true><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)),
                   (k_damp<false><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)));
@@ -587,7 +587,7 @@ static void backward_impl(const Launch &L, bool first, bool last, double *q, con
 void launch_backward(const Launch &L, bool first, bool last, double *q, const double *g, const double *y,
                      const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
                      double *alpha_out, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     if (L.streaming) backward_impl<true>(L, first, last, q, g, y, s_next, n, red_in, ys_j, gamma, alpha_out, out, grid);
     else backward_impl<false>(L, first, last, q, g, y, s_next, n, red_in, ys_j, gamma, alpha_out, out, grid);
@@ -608,7 +608,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
 void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
                     const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
                     int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, (last && owl) ? 2 : 4);
+    const int grid = grid_for(L, n, (last && owl) ? 2 : kU);
     count(L);
     const double *aux = last ? g_or_pg : y_next;
     if (L.streaming) forward_impl<true>(L, last, owl, r, s, aux, n, red_in, ys_j, alpha_in, start, end, goff, out, grid);
@@ -617,7 +617,7 @@ void launch_forward(const Launch &L, bool last, bool owl, double *r, const doubl
 
 void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t n, int64_t start, int64_t end,
                           int64_t goff, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_owl_constrain<true><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)),
                   (k_owl_constrain<false><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)));
@@ -625,7 +625,7 @@ void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t 
 
 template <int KIND>
 static void prim_impl(const Launch &L, double *out, const double *a, const double *b, double c, int64_t n) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_prim<true, KIND><<<grid, threads_for(L), 0, L.stream>>>({out, a, b, c}, n)),
                   (k_prim<false, KIND><<<grid, threads_for(L), 0, L.stream>>>({out, a, b, c}, n)));
@@ -638,7 +638,7 @@ void launch_veccpy(const Launch &L, double *y, const double *x, int64_t n, bool 
 }
 void launch_vecdiff(const Launch &L, double *z, const double *x, const double *y, int64_t n) { prim_impl<P_DIFF>(L, z, x, y, 0.0, n); }
 void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n, double *out) {
-    const int grid = grid_for(L, n, 4);
+    const int grid = grid_for(L, n, kU);
     count(L);
     LB_DISPATCH_S(L, (k_dot<true><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)),
                   (k_dot<false><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)));

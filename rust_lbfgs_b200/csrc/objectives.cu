@@ -59,13 +59,13 @@ struct RosenOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock(RosenOp<S> op, int64_t n, ReduceWs ws, double *fx) {
     double acc[1] = {0.0};
-    stream_pairs<1, 4>(n, op, acc);
+    stream_pairs<1, kUt>(n, op, acc);
     grid_reduce<1>(acc, ws, fx);
 }
 
 // Fused line-search trial for Rosenbrock (lbfgsb200_trial_eval_fn): x = xp + step*d, g = grad f(x) and
 // {f, g.d, g.g, x.x} in ONE pass, 2R 2W instead of K1 (2R 1W) + k_rosenbrock (1R 1W) + K2 (3R).  Same
-// per-element arithmetic, same tile shape (U = 4) and grid as those three kernels, so every sum sees the same
+// per-element arithmetic, same tile shape (kUt) and grid as those three kernels, so every sum sees the same
 // terms in the same order: the fused and unfused paths give bit-identical scalars.
 template <bool S>
 struct RosenTrialOp {
@@ -102,7 +102,7 @@ struct RosenTrialOp {
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_trial(RosenTrialOp<S> op, int64_t n, ReduceWs ws, double *out) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    stream_pairs<4, 4>(n, op, acc);
+    stream_pairs<4, kUt>(n, op, acc);
     grid_reduce<4>(acc, ws, out);
 }
 
@@ -236,9 +236,9 @@ __global__ void k_lj_energy_seq(const double *__restrict__ x, int64_t natoms, do
     *fx = e;
 }
 
-inline int stream_grid(const Objective *o, int64_t n) {
+inline int stream_grid(const Objective *o, int64_t n, int U = kU) {
     if (o->sequential) return 1;
-    const int64_t tile = (int64_t)kThreads * 4;
+    const int64_t tile = (int64_t)kThreads * U;
     int64_t tiles = ((n >> 1) + tile - 1) / tile;
     const int64_t cap = (int64_t)o->dev.sm_count * o->dev.blocks_per_sm;
     if (tiles > cap) tiles = cap;
@@ -251,7 +251,7 @@ int trial_impl(Objective *o, const double *xp, const double *d, double step, dou
     if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
     if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
-    const int grid = stream_grid(o, n);
+    const int grid = stream_grid(o, n, kUt);
     const int threads = o->sequential ? 1 : kThreads;
     // 4 vectors in flight per trial; the same L2 rule as the solver's (working set vs 0.75 L2)
     const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
@@ -265,7 +265,7 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
     switch (o->kind) {
         case OBJ_ROSENBROCK: {
             if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;  // the reference indexes x[i+1] (lib.rs:86)
-            const int grid = stream_grid(o, n);
+            const int grid = stream_grid(o, n, kUt);
             const int threads = o->sequential ? 1 : kThreads;
             const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
             if (streaming) k_rosenbrock<true><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);

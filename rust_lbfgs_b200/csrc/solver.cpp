@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace lb {
 
@@ -16,6 +17,16 @@ inline int env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
+struct DbgTimer {  // LBFGSB200_DEBUG_TIMING=1: wall time of the host-side phases to stderr
+    bool on = env_int("LBFGSB200_DEBUG_TIMING", 0) != 0;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lbfgsb200] %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 }  // namespace
 
 int query_device(int device, DeviceInfo *out) {
@@ -27,7 +38,7 @@ int query_device(int device, DeviceInfo *out) {
     out->device = device;
     out->sm_count = sm;
     out->l2_bytes = l2;
-    out->blocks_per_sm = env_int("LBFGSB200_BLOCKS_PER_SM", 4);
+    out->blocks_per_sm = env_int("LBFGSB200_BLOCKS_PER_SM", 1);  // tuned: see types.h
     if (out->blocks_per_sm < 1) out->blocks_per_sm = 1;
     if (out->blocks_per_sm > 16) out->blocks_per_sm = 16;
     return 0;
@@ -46,6 +57,59 @@ void free_reduce_ws(ReduceWs *ws) {
     ws->partials = nullptr;
     ws->ticket = nullptr;
 }
+
+// Small per-solver resources (device scalar slots, their pinned host mirror, the reduction workspace) are
+// recycled through a process-wide cache: on the B200 boxes a cudaFree / cudaFreeHost at solver destruction
+// sporadically blocked for 0.4 - 0.8 s (and cudaMallocHost for 80 ms), i.e. the cost of ~70 L-BFGS iterations at
+// n = 1e8.  lbfgsb200_trim_pool() releases the cache.
+namespace {
+struct Scratch {
+    int device = 0;
+    size_t scal_count = 0;
+    double *scal_dev = nullptr;
+    double *scal_host = nullptr;
+    ReduceWs ws{};
+};
+std::mutex g_scratch_mu;
+std::vector<Scratch> g_scratch;
+
+void scratch_free(Scratch &s) {
+    if (s.scal_dev) cudaFree(s.scal_dev);
+    if (s.scal_host) cudaFreeHost(s.scal_host);
+    free_reduce_ws(&s.ws);
+    s = Scratch();
+}
+
+int scratch_acquire(const DeviceInfo &dev, size_t scal_count, Scratch *out) {
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (size_t i = 0; i < g_scratch.size(); ++i) {
+            if (g_scratch[i].device == dev.device && g_scratch[i].scal_count >= scal_count &&
+                g_scratch[i].ws.stride >= dev.sm_count * 16) {
+                *out = g_scratch[i];
+                g_scratch.erase(g_scratch.begin() + i);
+                return 0;
+            }
+        }
+    }
+    Scratch s;
+    s.device = dev.device;
+    s.scal_count = scal_count < 256 ? 256 : scal_count;   // room for alpha[m] up to m ~ 200 without a re-allocation
+    if (cudaMalloc((void **)&s.scal_dev, sizeof(double) * s.scal_count) != cudaSuccess ||
+        cudaMallocHost((void **)&s.scal_host, sizeof(double) * kMaxAcc * 2) != cudaSuccess ||
+        alloc_reduce_ws(dev, &s.ws) != 0) {
+        scratch_free(s);
+        return LBFGSB200_ERR_CUDA;
+    }
+    *out = s;
+    return 0;
+}
+
+void scratch_release(const Scratch &s) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    g_scratch.push_back(s);
+}
+}  // namespace
 
 // The arena (2m + 4..5 n-vectors: 12.8 GB at n = 1e8, m = 6) comes from the device's default CUDA memory pool
 // with the release threshold lifted, so a process that solves repeatedly pays the driver's map/unmap of
@@ -76,19 +140,41 @@ int trim_pool(int device) {
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     if (cudaDeviceSynchronize() != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (size_t i = 0; i < g_scratch.size();) {
+            if (g_scratch[i].device == device) {
+                scratch_free(g_scratch[i]);
+                g_scratch.erase(g_scratch.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+    }
     return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
 Solver::~Solver() {
+    DbgTimer tm;
     for (auto &p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
     for (auto e : event_pool_) cudaEventDestroy(e);
+    tm.lap("destroy: events");
     if (arena_) {
         if (arena_pooled_) cudaFreeAsync(arena_, stream_);
         else cudaFree(arena_);
     }
-    if (scal_dev_) cudaFree(scal_dev_);
-    if (scal_host_) cudaFreeHost(scal_host_);
-    free_reduce_ws(&ws_);
+    tm.lap("destroy: arena");
+    if (scal_dev_) {  // back to the cache; make sure nothing of ours is still running on these buffers
+        cudaStreamSynchronize(stream_);
+        Scratch sc;
+        sc.device = dev_.device;
+        sc.scal_count = scal_count_;
+        sc.scal_dev = scal_dev_;
+        sc.scal_host = scal_host_;
+        sc.ws = ws_;
+        scratch_release(sc);
+    }
+    tm.lap("destroy: scalars + workspace");
 }
 
 int Solver::fail(int status, const char *msg) {
@@ -146,6 +232,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     ls_.max_linesearch = p.ls_max_linesearch;
     ls_.gradient_only = p.ls_gradient_only != 0;
 
+    DbgTimer tm;
     int rc = query_device(device, &dev_);
     if (rc != 0) return fail(rc, "no usable CUDA device (this library has no CPU fallback)");
     cudaError_t e = cudaSetDevice(device);
@@ -159,6 +246,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     if (arena_pooled_) e = cudaMallocAsync(&arena_, (size_t)(nvec * vec_bytes + wp_bytes), stream_);
     else e = cudaMalloc(&arena_, (size_t)(nvec * vec_bytes + wp_bytes));
     if (e != cudaSuccess) { arena_ = nullptr; return cuda_fail(e, "cudaMalloc(arena)"); }
+    tm.lap("create: arena");
     char *base = (char *)arena_;
     auto take = [&]() { double *r = (double *)base; base += vec_bytes; return r; };
     xbuf_[1] = take();
@@ -172,16 +260,20 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     if (owl_) wp_ = (signed char *)base;
     ys_.assign(m_, 0.0);
 
-    const size_t scal_bytes = sizeof(double) * (SLOT_COUNT * kMaxAcc + (size_t)m_);
-    e = cudaMalloc((void **)&scal_dev_, scal_bytes);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scalars)");
-    e = cudaMemset(scal_dev_, 0, scal_bytes);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(scalars)");
+    const size_t scal_need = SLOT_COUNT * kMaxAcc + (size_t)m_;
+    Scratch sc;
+    rc = scratch_acquire(dev_, scal_need, &sc);
+    if (rc != 0) return fail(rc, "cudaMalloc(scalars / pinned mirror / reduce workspace)");
+    scal_dev_ = sc.scal_dev;
+    scal_host_ = sc.scal_host;
+    scal_count_ = sc.scal_count;
+    ws_ = sc.ws;
+    e = cudaMemsetAsync(scal_dev_, 0, sizeof(double) * scal_need, stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scalars)");
+    e = cudaMemsetAsync(ws_.ticket, 0, 256, stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ticket)");
     alpha_dev_ = scal_dev_ + SLOT_COUNT * kMaxAcc;
-    e = cudaMallocHost((void **)&scal_host_, sizeof(double) * kMaxAcc * 2);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-    rc = alloc_reduce_ws(dev_, &ws_);
-    if (rc != 0) return fail(rc, "cudaMalloc(reduce workspace)");
+    tm.lap("create: scalars + pinned + workspace");
 
     // evict-first accesses once the working set cannot live in L2
     const double working_set = (double)(nvec + 1) * (double)vec_bytes;
@@ -597,7 +689,9 @@ int Solver::minimize(double *x_dev, lbfgsb200_eval_fn eval, void *user, lbfgsb20
         if (rc != 0) { status = rc; break; }
         if (prog && prog(prog_user, &pr) != 0) { status = LBFGSB200_OK_CANCELLED; break; }
     }
+    auto t2 = now();
     int frc = finish();
+    if (dbg) fprintf(stderr, "[lbfgsb200] finish %.3f ms\n", ms(t2, now()));
     if (frc != 0 && status >= 0) status = frc;
     last_status_ = status;
     report(rep);

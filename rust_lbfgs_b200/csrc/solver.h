@@ -31,7 +31,7 @@ struct DeviceInfo {
     int device = 0;
     int sm_count = 148;
     int64_t l2_bytes = 126ll << 20;
-    int blocks_per_sm = 4;
+    int blocks_per_sm = 1;   // CTAs per SM in a full grid (LBFGSB200_BLOCKS_PER_SM); tuned, see types.h
 };
 int query_device(int device, DeviceInfo *out);
 // returns the pages cached by the solver arenas' memory pool to the driver
@@ -111,6 +111,7 @@ class Solver {
     double *scal_dev_ = nullptr;    // SLOT_COUNT * kMaxAcc doubles, then alpha[m]
     double *alpha_dev_ = nullptr;
     double *scal_host_ = nullptr;   // pinned mirror of one slot
+    size_t scal_count_ = 0;         // doubles behind scal_dev_ (the buffers are recycled, see solver.cpp)
     ReduceWs ws_{};
     int cur_x_ = 0, cur_g_ = 0;
 

@@ -5,9 +5,32 @@
 
 namespace lb {
 
-constexpr int kThreads = 256;          // threads per CTA for every streaming kernel
+#ifndef LB_THREADS
+#define LB_THREADS 256
+#endif
+constexpr int kThreads = LB_THREADS;   // threads per CTA for every streaming kernel
 constexpr int kWarps = kThreads / 32;
-constexpr int kMinBlocks = 4;         // resident CTAs per SM every kernel is compiled for (<= 64 registers)
+#ifndef LB_MINBLOCKS
+#define LB_MINBLOCKS 2
+#endif
+#ifndef LB_U
+#define LB_U 8
+#endif
+#ifndef LB_UH
+#define LB_UH 4
+#endif
+#ifndef LB_UT
+#define LB_UT 6
+#endif
+constexpr int kUt = LB_UT;             // the same for the fused trial kernel (2R 2W) and, so that the fused and the
+                                       // unfused paths sum the same terms in the same order, K2 and the objective
+constexpr int kUh = LB_UH;             // the same for the history kernel (5 input vectors)
+// Tile shapes, tuned on B200 at n = 1e8 (profiles/r01_tuning.md): one 256-thread CTA per SM with 8 independent
+// 128-bit loads per input vector in flight per thread (2048 per SM per vector) streams 3R 1W at ~7.0 TB/s; more
+// resident CTAs or deeper unrolling lose 5-7 %.  The 2R 2W fused trial is best with 24 KB (non power of two)
+// tiles, the 4R 2W history kernel with 16 KB tiles.
+constexpr int kMinBlocks = LB_MINBLOCKS;  // resident CTAs per SM every kernel is compiled for (2 => <= 128 registers)
+constexpr int kU = LB_U;               // independent 128-bit loads per input vector per thread (tile = kU * 4 KB)
 constexpr int kMaxAcc = 8;             // accumulators per kernel (and doubles per scalar slot)
 
 // Per-solver reduction workspace in HBM.
