@@ -343,8 +343,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=float, default=1e8, help="elements per GPU")
-    ap.add_argument("--m", type=int, default=6)
+    # (--elems / --history: torchrun's own parser chokes on "--n" / "--m" as ambiguous abbreviations)
+    ap.add_argument("--n", "--elems", dest="n", type=float, default=1e8, help="elements per GPU")
+    ap.add_argument("--m", "--history", dest="m", type=int, default=6)
     ap.add_argument("--ref-n", type=float, default=5e6, help="--impl reference: sample size")
     ap.add_argument("--cpu-n", type=float, default=1e7, help="cpu_baseline sample size")
     ap.add_argument("--cpu-steps", type=int, default=6)
