@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "../../include/lbfgsb200.h"
@@ -33,6 +34,8 @@ struct Objective {
     double *t = nullptr;         // per-row residual
     double *gpart = nullptr;     // [row_chunks][ncol] partial gradients
     int row_chunks = 0;
+    double *gfused = nullptr;    // [sm_count][ncol] per-CTA partial gradients of the fused one-pass kernel
+    bool fused = true;           // LBFGSB200_GLM_FUSED=0 forces the two-pass kernels
     // LJ
     double eps = 1.0, sigma = 1.0;
 };
@@ -175,6 +178,188 @@ __global__ void __launch_bounds__(kThreads) k_glm_grad_final(const double *__res
     g[c] = a;
 }
 
+
+// ---- GLM, fused: ONE pass over X ---------------------------------------------------------------------
+// z_r = X[r,:].w, the per-row loss term and residual t_r, and the gradient update g += t_r X[r,:] all while
+// row r is on chip, so X (80 GB at 1e6 x 1e4) crosses HBM once per evaluation instead of twice.
+//   * one 256-thread CTA per SM owns rows r = blockIdx.x, + gridDim.x, ...
+//   * rows are staged in shared memory by 1-D TMA bulk copies (cp.async.bulk -> mbarrier complete_tx), a ring
+//     of `stages` row buffers so the next rows are in flight while this one is consumed (2 stages of 80 KB at
+//     ncol = 1e4, more for shorter rows);
+//   * every thread owns KP fixed column pairs: its slice of w and its slice of the gradient accumulator live in
+//     registers for the whole kernel; the row is read from shared memory twice (dot, then axpy);
+//   * per-CTA partial gradients go to gpart[cta][ncol] and are summed in CTA order by k_glm_grad_final;
+//     f goes through the usual deterministic two-level reduction.
+// Requires ncol even (16-byte aligned rows) and ncol <= 512 * KP; other shapes use the two-pass kernels above.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kGlmMaxStages = 8;
+constexpr uint32_t kTmaChunk = 32768;  // bytes per bulk copy
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1)
+k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const double *__restrict__ w,
+            double *__restrict__ gpart, int64_t nrow, int64_t ncol, int kind, int stages, uint32_t row_stride,
+            ReduceWs ws, double *fx) {
+    extern __shared__ __align__(128) unsigned char glm_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kGlmMaxStages];
+    __shared__ double red[2][kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t npairs = ncol >> 1;
+    const uint32_t row_bytes = (uint32_t)(ncol * 8);
+    const int64_t my_rows = (nrow > (int64_t)blockIdx.x) ? (nrow - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    double2 wv[KP], gv[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int64_t p = tid + (int64_t)k * kThreads;
+        wv[k] = (p < npairs) ? reinterpret_cast<const double2 *>(w)[p] : make_double2(0.0, 0.0);
+        gv[k] = make_double2(0.0, 0.0);
+    }
+    auto issue = [&](int64_t i) {  // thread 0: stage row i of this CTA
+        const int s = (int)(i % stages);
+        const double *src = X + (blockIdx.x + i * gridDim.x) * ncol;
+        unsigned char *dst = glm_smem + (size_t)s * row_stride;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer
+        mbar_expect_tx(&full_bar[s], row_bytes);
+        for (uint32_t off = 0; off < row_bytes; off += kTmaChunk) {
+            const uint32_t nb = (row_bytes - off < kTmaChunk) ? (row_bytes - off) : kTmaChunk;
+            tma_load_1d(dst + off, reinterpret_cast<const unsigned char *>(src) + off, nb, &full_bar[s]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int64_t i = 0; i < stages && i < my_rows; ++i) issue(i);
+
+    double facc = 0.0;
+    double y_next = (my_rows > 0 && lane == 0) ? y[blockIdx.x] : 0.0;
+    for (int64_t i = 0; i < my_rows; ++i) {
+        const int s = (int)(i % stages);
+        const uint32_t parity = (uint32_t)((i / stages) & 1);
+        const double yr = y_next;
+        if (lane == 0 && i + 1 < my_rows) y_next = y[blockIdx.x + (i + 1) * gridDim.x];
+        mbar_wait(&full_bar[s], parity);
+        const double2 *row = reinterpret_cast<const double2 *>(glm_smem + (size_t)s * row_stride);
+        double part = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int64_t p = tid + (int64_t)k * kThreads;
+            if (p < npairs) {
+                const double2 xv = row[p];
+                part += wv[k].x * xv.x;
+                part += wv[k].y * xv.y;
+            }
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[i & 1][warp] = part;
+        __syncthreads();
+        double z = 0.0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) z += red[i & 1][q];
+        double t = 0.0;
+        if (lane == 0) {  // one lane per warp evaluates the link function; f is accumulated once per CTA
+            double term;
+            if (kind == 0) {
+                const double e = exp(z);
+                term = yr * z - e;
+                t = yr - e;
+            } else {
+                const double sp = fmax(z, 0.0) + log1p(exp(-fabs(z)));
+                double mu;
+                if (z >= 0.0) mu = 1.0 / (1.0 + exp(-z));
+                else { const double e = exp(z); mu = e / (1.0 + e); }
+                term = sp - yr * z;
+                t = mu - yr;
+            }
+            if (warp == 0) facc += term;
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (kind == 0) t = -t;  // g = (-X^T) t, tests/owlqn.rs:40
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int64_t p = tid + (int64_t)k * kThreads;
+            if (p < npairs) {
+                const double2 xv = row[p];
+                gv[k].x += t * xv.x;
+                gv[k].y += t * xv.y;
+            }
+        }
+        __syncthreads();  // every thread is done with stage s: it may be refilled
+        if (tid == 0 && i + stages < my_rows) issue(i + stages);
+    }
+    double *gp = gpart + (int64_t)blockIdx.x * ncol;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int64_t p = tid + (int64_t)k * kThreads;
+        if (p < npairs) reinterpret_cast<double2 *>(gp)[p] = gv[k];
+    }
+    double acc[1] = {(kind == 0) ? -1.0 * facc : facc};
+    grid_reduce<1>(acc, ws, fx);
+}
+
+template <int KP>
+int launch_glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
+    const uint32_t row_bytes = (uint32_t)(o->ncol * 8);
+    const uint32_t row_stride = (row_bytes + 127u) & ~127u;
+    int stages = (int)((200u * 1024u) / row_stride);
+    if (stages > kGlmMaxStages) stages = kGlmMaxStages;
+    if (stages < 2) return LBFGSB200_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)stages * row_stride;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_glm_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return LBFGSB200_ERR_CUDA;
+        attr_set = true;
+    }
+    int grid = o->dev.sm_count;
+    if ((int64_t)grid > o->nrow) grid = (int)o->nrow;
+    k_glm_fused<KP><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind, stages,
+                                                       row_stride, o->ws, fx);
+    const unsigned cb = (unsigned)((o->ncol + kThreads - 1) / kThreads);
+    k_glm_grad_final<<<cb, kThreads, 0, stream>>>(o->gfused, g, o->ncol, grid);
+    return 0;
+}
+
+// 0 = launched; LBFGSB200_ERR_UNSUPPORTED = shape not covered (caller falls back to the two-pass kernels)
+int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
+    if (!o->gfused || (o->ncol & 1) || (((uintptr_t)o->X | (uintptr_t)w) & 15u)) return LBFGSB200_ERR_UNSUPPORTED;
+    const int64_t need = (o->ncol / 2 + kThreads - 1) / kThreads;  // column pairs per thread
+    if (need <= 1) return launch_glm_fused<1>(o, w, g, stream, fx);
+    if (need <= 2) return launch_glm_fused<2>(o, w, g, stream, fx);
+    if (need <= 4) return launch_glm_fused<4>(o, w, g, stream, fx);
+    if (need <= 8) return launch_glm_fused<8>(o, w, g, stream, fx);
+    if (need <= 12) return launch_glm_fused<12>(o, w, g, stream, fx);
+    if (need <= 16) return launch_glm_fused<16>(o, w, g, stream, fx);
+    if (need <= 20) return launch_glm_fused<20>(o, w, g, stream, fx);
+    return LBFGSB200_ERR_UNSUPPORTED;
+}
+
 // ---- Lennard-Jones: thread = atom, partners streamed through shared memory in index order -----
 // For atom i the reference adds its pair forces in ascending partner order (pairs (i, j<i) during
 // row i, then pairs (i', i) for i' > i), and (p_i - p_j) == -(p_j - p_i) exactly, so a sequential
@@ -278,6 +463,11 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
             break;
         case OBJ_GLM: {
             if (n != o->ncol) return LBFGSB200_ERR_INVALID_PARAM;
+            if (o->fused) {
+                const int frc = glm_fused(o, x, g, stream, fx);
+                if (frc == 0) break;
+                if (frc != LBFGSB200_ERR_UNSUPPORTED) return frc;
+            }
             int64_t blocks = (o->nrow + kWarps - 1) / kWarps;
             const int64_t cap = (int64_t)o->dev.sm_count * 8;
             if (blocks > cap) blocks = cap;
@@ -346,8 +536,11 @@ int lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const dou
     if (chunks > want) chunks = want;
     if (chunks < 1) chunks = 1;
     o->row_chunks = chunks;
+    const char *fenv = getenv("LBFGSB200_GLM_FUSED");
+    o->fused = !(fenv && fenv[0] == '0');
     if (cudaMalloc((void **)&o->t, sizeof(double) * (size_t)nrow) != cudaSuccess ||
-        cudaMalloc((void **)&o->gpart, sizeof(double) * (size_t)chunks * (size_t)ncol) != cudaSuccess) {
+        cudaMalloc((void **)&o->gpart, sizeof(double) * (size_t)chunks * (size_t)ncol) != cudaSuccess ||
+        cudaMalloc((void **)&o->gfused, sizeof(double) * (size_t)o->dev.sm_count * (size_t)ncol) != cudaSuccess) {
         lbfgsb200_objective_destroy(reinterpret_cast<lbfgsb200_objective_t *>(o));
         return LBFGSB200_ERR_CUDA;
     }
@@ -385,6 +578,7 @@ void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
     if (!o) return;
     if (o->t) cudaFree(o->t);
     if (o->gpart) cudaFree(o->gpart);
+    if (o->gfused) cudaFree(o->gfused);
     lb::free_reduce_ws(&o->ws);
     delete o;
 }

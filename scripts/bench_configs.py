@@ -1,0 +1,140 @@
+"""Secondary measurements: BASELINE.json configs[0], [2], [3] (the headline bench.py covers [1] and [4]).
+
+    python scripts/bench_configs.py [--full] [--only cfg1,cfg3,cfg4,small]
+
+Each line is a JSON record {config, n, wall_s, iterations, evaluations, it_per_s, ...}.  Synthetic data per
+SURVEY.md §8(d).  --full uses the full sizes (1e6 x 1e4 GLM = 80 GB of X; 1e5 LJ atoms); the default sizes
+finish in seconds."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import rust_lbfgs_b200 as R
+
+DEV = torch.device("cuda", 0)
+
+
+def sync_time():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+def solve(builder, x, obj, tag, extra=None, max_iter=None):
+    if max_iter:
+        builder = builder.with_max_iterations(max_iter)
+    ncalls = []
+    t0 = sync_time()
+    try:
+        rep = builder.minimize(x, obj, lambda p: ncalls.append(p.ncall) and False)
+        status = rep.status_name
+    except R.LbfgsError as e:
+        rep, status = e.report, e.status_name
+    t1 = sync_time()
+    rec = dict(config=tag, n=int(x.numel()), wall_s=t1 - t0, status=status, iterations=len(ncalls) - 1,
+               evaluations=rep.neval, fx=rep.fx, gnorm=rep.gnorm,
+               it_per_s=(len(ncalls) - 1) / (t1 - t0), ms_per_evaluation=1e3 * (t1 - t0) / max(1, rep.neval))
+    rec.update(extra or {})
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
+def cfg1():
+    """examples/sample.rs: Rosenbrock N=100, defaults."""
+    x = torch.empty(100, dtype=torch.float64, device=DEV)
+    for rep in range(2):  # second run: warm
+        x[0::2], x[1::2] = -1.2, 1.0
+        solve(R.lbfgs(), x, R.Rosenbrock(), f"cfg1 rosenbrock n=100 (run {rep})")
+
+
+def small_n():
+    """launch-latency regime: Rosenbrock at n = 1e4 .. 1e7, 40 iterations."""
+    for n in (10_000, 300_000, 1_000_000, 10_000_000):
+        x = torch.empty(n, dtype=torch.float64, device=DEV)
+        x[0::2], x[1::2] = -1.2, 1.0
+        solve(R.lbfgs(), x, R.Rosenbrock(), f"rosenbrock n={n}", max_iter=41)
+
+
+def make_glm(nrow, ncol, seed=2024):
+    """X: column 0 = 1, others N(0,1); w* 1% non-zeros; y ~ Bernoulli(sigmoid(X w*)).  Generated on the device in
+    row chunks (80 GB at the full size)."""
+    g = torch.Generator(device=DEV)
+    g.manual_seed(seed)
+    X = torch.empty((nrow, ncol), dtype=torch.float64, device=DEV)
+    wstar = torch.zeros(ncol, dtype=torch.float64, device=DEV)
+    nz = max(1, ncol // 100)
+    idx = torch.randperm(ncol, generator=g, device=DEV)[:nz]
+    wstar[idx] = torch.randn(nz, generator=g, device=DEV, dtype=torch.float64)
+    y = torch.empty(nrow, dtype=torch.float64, device=DEV)
+    chunk = max(1, min(nrow, (1 << 28) // ncol))
+    for r0 in range(0, nrow, chunk):
+        r1 = min(nrow, r0 + chunk)
+        X[r0:r1].normal_(generator=g)
+        X[r0:r1, 0] = 1.0
+        p = torch.sigmoid(X[r0:r1] @ wstar)
+        y[r0:r1] = (torch.rand(r1 - r0, generator=g, device=DEV, dtype=torch.float64) < p).to(torch.float64)
+    return X, y
+
+
+def cfg3(full):
+    """OWL-QN L1-regularised logistic regression, intercept unpenalised (start = 1), mirrors tests/owlqn.rs:46-49."""
+    nrow, ncol = (1_000_000, 10_000) if full else (100_000, 2_000)
+    X, y = make_glm(nrow, ncol)
+    obj = R.Glm("logistic", X, y)
+    w = torch.zeros(ncol, dtype=torch.float64, device=DEV)
+    gx = torch.empty_like(w)
+    # objective alone
+    import ctypes as C
+    L = R.lib()
+    fx = torch.zeros(1, dtype=torch.float64, device=DEV)
+    st = int(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        L.lbfgsb200_objective_eval(obj._user_ptr(0), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
+    t0 = sync_time()
+    reps = 5
+    for _ in range(reps):
+        L.lbfgsb200_objective_eval(obj._user_ptr(0), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
+    t1 = sync_time()
+    xbytes = 8.0 * nrow * ncol
+    print(json.dumps(dict(config=f"cfg3 glm objective alone {nrow}x{ncol}", ms_per_evaluation=1e3 * (t1 - t0) / reps,
+                          X_GB=xbytes / 1e9, GBps_one_pass_equivalent=xbytes / 1e9 / ((t1 - t0) / reps))), flush=True)
+    c = 1.0 * nrow / 500.0   # tests/owlqn.rs uses c = 1 with 500 rows
+    solve(R.lbfgs().with_orthantwise(c, 1).with_epsilon(1e-4), w, obj, f"cfg3 owlqn logistic {nrow}x{ncol} c={c}",
+          extra=dict(X_GB=xbytes / 1e9), max_iter=60)
+    print(json.dumps(dict(config="cfg3 sparsity", nonzeros=int((w != 0).sum()), ncol=ncol)), flush=True)
+
+
+def cfg4(full):
+    """Lennard-Jones cluster on a jittered simple-cubic lattice (spacing 1.12, jitter 0.05, seed 7)."""
+    side = 47 if full else 16           # 47^3 = 103823 ~ 1e5 atoms
+    rng = np.random.default_rng(7)
+    g = np.arange(side, dtype=np.float64) * 1.12
+    p = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    p += rng.uniform(-0.05, 0.05, p.shape)
+    na = p.shape[0]
+    for tag, b in (("gradient-only max_linesearch=2", R.lbfgs().with_gradient_only().with_max_linesearch(2)),
+                   ("damped", R.lbfgs().with_damping(True))):
+        x = torch.tensor(p.ravel(), dtype=torch.float64, device=DEV)
+        solve(b, x, R.LennardJones(), f"cfg4 lj {na} atoms {tag}", extra=dict(pairs=na * (na - 1) // 2),
+              max_iter=21 if full else 41)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default="cfg1,small,cfg3,cfg4")
+    a = ap.parse_args()
+    which = a.only.split(",")
+    if "cfg1" in which:
+        cfg1()
+    if "small" in which:
+        small_n()
+    if "cfg4" in which:
+        cfg4(a.full)
+    if "cfg3" in which:
+        cfg3(a.full)
