@@ -213,7 +213,10 @@ def run_ours(args):
     state.propagate()                       # propagate #1 is the reference's no-op (src/lbfgs.rs:507-510)
     for _ in range(W):
         state.propagate()
-    state.profile_enable(True)
+    # CUDA events around the dominant kernel only inside the timed region (events around every launch cost
+    # ~2 % at n = 1e8); the other kernels are timed in a separate pass after it
+    DOM = "backward"
+    state.profile_enable(True, kinds=[DOM])
     state.profile_reset()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -233,6 +236,13 @@ def run_ours(args):
     ms_total = D.max_over_ranks(ev0.elapsed_time(ev1))
     prof = state.profile()
     final = state.report()
+    # per-kernel profile pass (NOT part of `value`): a few more iterations with events around every launch
+    state.profile_enable(True)
+    state.profile_reset()
+    P = max(3, min(10, K))
+    for _ in range(P):
+        state.propagate()
+    prof_all = state.profile()
     state.finish()
     state.close()
 
@@ -242,7 +252,7 @@ def run_ours(args):
     value = it_per_s * n_global / N_REF
 
     peak, peak_src = load_peaks()
-    dom = "backward" if launches["backward"] >= launches["forward"] else "forward"
+    dom = DOM
     dom_gbs = (kbytes[dom] / 1e9) / (kms[dom] / 1e3) if kms[dom] > 0 else None
     traffic = load_traffic()
     roofline = {
@@ -266,8 +276,13 @@ def run_ours(args):
         "survey_formula_equivalent_GBps": surv_bytes / 1e9 / (ms_total / 1e3),
         "fused_trial": bool(launches.get("trial_eval", 0) > 0),
         "evaluations_per_iteration": (launches["evaluate"] + launches.get("trial_eval", 0)) / max(1, K),
-        "kernel_ms": {k: round(v, 3) for k, v in kms.items() if v > 0},
-        "kernel_GBps": {k: round(kbytes[k] / 1e9 / (kms[k] / 1e3), 1) for k in kms if kms[k] > 0 and kbytes[k] > 0},
+        "kernel_ms_timed_region": {k: round(v, 3) for k, v in kms.items() if v > 0},
+        "profile_pass": {
+            "note": f"{P} extra iterations after the timed region with CUDA events around every launch",
+            "kernel_ms": {k: round(v, 3) for k, v in prof_all["ms"].items() if v > 0},
+            "kernel_GBps": {k: round(prof_all["bytes"][k] / 1e9 / (prof_all["ms"][k] / 1e3), 1) for k in prof_all["ms"]
+                            if prof_all["ms"][k] > 0 and prof_all["bytes"][k] > 0},
+        },
         "host_syncs": prof["host_syncs"], "allreduces": prof["allreduces"],
     }
     del x

@@ -181,7 +181,7 @@ int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int6
 
 int lbfgsb200_profile_enable(lbfgsb200_solver_t *solver, int timing) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
-    S(solver)->profile_enable(timing != 0);
+    S(solver)->profile_enable(timing);
     return 0;
 }
 int lbfgsb200_profile_get(lbfgsb200_solver_t *solver, lbfgsb200_profile_t *out) {

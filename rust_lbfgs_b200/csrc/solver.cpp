@@ -298,7 +298,7 @@ Launch Solver::launch_cfg() {
 
 // ---- instrumentation -----------------------------------------------------------------------
 void Solver::prof_begin(int kind) {
-    if (!timing_) return;
+    if (!timing_ || !((timing_mask_ >> kind) & 1u)) return;
     Pending p;
     p.kind = kind;
     for (cudaEvent_t *ev : {&p.a, &p.b}) {
@@ -311,7 +311,7 @@ void Solver::prof_begin(int kind) {
 void Solver::prof_end(int kind, double bytes) {
     prof_.launches[kind] += 1;
     prof_.bytes[kind] += bytes;
-    if (!timing_) return;
+    if (!timing_ || !((timing_mask_ >> kind) & 1u)) return;
     cudaEventRecord(pending_.back().b, stream_);
 }
 void Solver::prof_resolve() {

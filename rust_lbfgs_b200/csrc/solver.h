@@ -63,7 +63,8 @@ class Solver {
     // optional fused trial evaluate (lbfgsb200_trial_eval_fn); ignored for OWL-QN
     void set_trial_evaluate(lbfgsb200_trial_eval_fn fn, void *user) { trial_eval_ = fn; trial_user_ = user; }
 
-    void profile_enable(bool timing) { timing_ = timing; }
+    // timing: 0 = off, 1 = every kernel kind, otherwise a mask: bit (1 + kind) times LBFGSB200_K_<kind> only
+    void profile_enable(int timing) { timing_ = timing != 0; timing_mask_ = (timing == 1) ? ~0u : ((unsigned)timing >> 1); }
     void profile_get(lbfgsb200_profile_t *out);
     void profile_reset();
 
@@ -132,6 +133,7 @@ class Solver {
 
     // profile
     bool timing_ = false;
+    unsigned timing_mask_ = ~0u;
     lbfgsb200_profile_t prof_{};
     std::vector<Pending> pending_;
     std::vector<cudaEvent_t> event_pool_;

@@ -13,7 +13,7 @@ x[1::2] = 1.0
 st = R.lbfgs().with_m(int(os.environ.get("TUNE_M", "6"))).build(x, R.Rosenbrock())
 for _ in range(8):
     st.propagate()
-st.profile_enable(True)
+st.profile_enable(os.environ.get("TUNE_TIMING", "1") != "0")
 st.profile_reset()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -23,5 +23,6 @@ torch.cuda.synchronize()
 t1 = time.perf_counter()
 p = st.profile()
 gbps = {k: round(p["bytes"][k] / 1e9 / (p["ms"][k] / 1e3)) for k in p["ms"] if p["ms"][k] > 0 and p["bytes"][k] > 0}
+gbps["all_bytes_over_wall_GBps"] = round(sum(p["bytes"].values()) / 1e9 / (t1 - t0))
 kms = sum(p["ms"].values())
 print(f"{os.environ.get('TUNE_TAG', '')} it/s={iters / (t1 - t0):.2f} kernel_ms/it={kms / iters:.3f} wall_ms/it={1e3 * (t1 - t0) / iters:.3f} {gbps}", flush=True)
