@@ -28,6 +28,8 @@ if ROOT not in sys.path:
 N_REF = 100_000_000
 METRIC = "lbfgs_iterations_per_sec_at_n1e8"
 UNIT = "it/s"
+WORKLOAD = ("Rosenbrock n=1e8 f64 per GPU, m=6, MoreThuente, device-resident evaluate "
+            "(BASELINE.json configs[1])")
 
 
 def load_peaks():
@@ -64,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -73,9 +75,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Samples that arrived inside [t_begin, t_end] (the timed region); all samples if that leaves none."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,7 +87,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.15)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows], "whole run (no sample fell inside the timed region)"
+        for r in rows:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 9:
                 continue
@@ -99,7 +106,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def algorithmic_bytes_survey(n, launches, kbytes):
@@ -155,8 +163,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done * (N_REF / n_sample),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Rosenbrock n=1e8 f64 m=6 MoreThuente (BASELINE.json configs[1]), CPU oracle port",
-                   "n_sample": n_sample, "m": args.m},
+        "config": {"workload": WORKLOAD, "n_per_gpu": N_REF, "n_global": N_REF, "m": args.m, "linesearch": "MoreThuente",
+                   "reference_arm": "CPU oracle port (the reference is Rust; no rustc here), 1 thread as the reference",
+                   "n_sample": n_sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,6 +218,9 @@ def run_ours(args):
     # ---- device-resident run: `value`, roofline ------------------------------------------------
     x = torch.empty(n_local, dtype=torch.float64, device=dev)
     fill_x0(x)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                     # nvidia-smi needs ~0.5 s to produce its first sample: start it early
     state = make_builder().build(x, obj)
     state.propagate()                       # propagate #1 is the reference's no-op (src/lbfgs.rs:507-510)
     for _ in range(W):
@@ -218,12 +230,10 @@ def run_ours(args):
     DOM = "backward"
     state.profile_enable(True, kinds=[DOM])
     state.profile_reset()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
+    wall_begin = time.time()
     ev0.record()
     ncalls = []
     for _ in range(K):
@@ -231,8 +241,9 @@ def run_ours(args):
         ncalls.append(p.ncall)
     ev1.record()
     torch.cuda.synchronize()
+    wall_end = time.time()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall_begin, wall_end) if rank == 0 else None
     ms_total = D.max_over_ranks(ev0.elapsed_time(ev1))
     prof = state.profile()
     final = state.report()
@@ -337,8 +348,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Rosenbrock n=1e8 f64 per GPU, m=6, MoreThuente, device-resident evaluate "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD if (n_local == N_REF and m == 6) else
+                       f"Rosenbrock n={n_local} f64 per GPU, m={m}, MoreThuente, device-resident evaluate",
                        "n_per_gpu": n_local, "n_global": n_global, "m": m, "linesearch": "MoreThuente",
                        "l2_policy": "inputs larger than L2 (19 vectors x 0.8 GB vs 126 MB)",
                        "ncall_per_iteration": ncalls, "final_fx": final.fx, "final_gnorm": final.gnorm},
