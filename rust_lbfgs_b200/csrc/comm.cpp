@@ -1,5 +1,13 @@
-// comm.cpp — one NCCL rank per process/GPU, used for exactly one thing: summing a handful of f64
-// partial dot products over the ranks after each fused reduction step.
+// comm.cpp — one rank per process/GPU, used for exactly one thing: summing a handful of f64 partial dot
+// products over the ranks after each fused reduction step.
+//
+// Two transports.  (1) The default on an NVLink/NVSwitch box: PEER MAILBOXES — every rank allocates a small
+// mailbox ring in its HBM, the ranks exchange CUDA IPC handles once (over NCCL, at communicator creation) and
+// map each other's mailboxes; from then on the all-reduce happens INSIDE the reducing kernels (reduce.cuh:
+// peer_allreduce — peer stores over NVLink, fixed rank-order sum), with no collective call and no extra launch.
+// (2) ncclAllReduce(ncclDouble, ncclSum) per step: the fallback when IPC mapping is unavailable, or with
+// LBFGSB200_PEER_REDUCE=0.  Both give bit-identical results on every rank, which the replicated scalar
+// line-search logic relies on.
 //
 // libnccl.so.2 is resolved with dlopen at first use, so the single-GPU path has no NCCL
 // dependency at all and a process that already loaded torch's bundled NCCL shares that copy.
@@ -9,8 +17,10 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/lbfgsb200.h"
 #include "solver.h"
@@ -31,6 +41,7 @@ struct Nccl {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -49,6 +60,7 @@ Nccl &nccl() {
         n.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(n.handle, "ncclCommInitRank");
         n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
         n.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
+        n.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllGather");
         n.GetErrorString = (const char *(*)(int))dlsym(n.handle, "ncclGetErrorString");
         n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce;
     });
@@ -60,10 +72,78 @@ Nccl &nccl() {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1, device = 0;
+    // peer mailboxes (transport 1)
+    PeerCtx peer{};                    // nranks == 0: not available, use NCCL
+    unsigned long long seq = 0;        // exchange counter, advanced identically on every rank
+    double *mailbox = nullptr;         // this rank's ring: kMailRing x nranks entries of kMailStride doubles
+    void *opened[kMaxPeers] = {};
 };
 
 int comm_rank(const Comm *c) { return c ? c->rank : 0; }
 int comm_size(const Comm *c) { return c ? c->nranks : 1; }
+const PeerCtx *comm_peer(const Comm *c) { return (c && c->peer.nranks > 1) ? &c->peer : nullptr; }
+unsigned long long *comm_peer_seq(Comm *c) { return c ? &c->seq : nullptr; }
+
+namespace {
+// Maps every rank's mailbox into this process.  Collective; returns false (on every rank) if any rank failed.
+bool setup_peer_mailboxes(Comm *c) {
+    Nccl &n = nccl();
+    const char *env = getenv("LBFGSB200_PEER_REDUCE");
+    bool ok = !(env && env[0] == '0') && n.AllGather && c->nranks <= kMaxPeers;
+    const size_t bytes = sizeof(double) * kMailRing * (size_t)c->nranks * kMailStride;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) ok = cudaMalloc((void **)&c->mailbox, bytes) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->mailbox, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->mailbox) == cudaSuccess;
+    // all-gather the handles (+ one status byte per rank) through NCCL
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 16;
+    unsigned char *dev = nullptr;
+    std::vector<unsigned char> host(rec * c->nranks, 0);
+    if (cudaMalloc((void **)&dev, rec * c->nranks) != cudaSuccess) return false;  // cannot even talk: caller falls back
+    memcpy(&host[rec * c->rank], &mine, sizeof(mine));
+    host[rec * c->rank + sizeof(mine)] = ok ? 1 : 0;
+    cudaMemcpy(dev, host.data(), rec * c->nranks, cudaMemcpyHostToDevice);
+    bool talk = n.AllGather && n.AllGather(dev + rec * c->rank, dev, rec, /*ncclChar*/ 0, c->comm, nullptr) == ncclSuccess &&
+                cudaDeviceSynchronize() == cudaSuccess;
+    if (talk) cudaMemcpy(host.data(), dev, rec * c->nranks, cudaMemcpyDeviceToHost);
+    bool all_ok = talk;
+    for (int r = 0; all_ok && r < c->nranks; ++r) all_ok = host[rec * r + sizeof(mine)] == 1;
+    if (all_ok) {
+        for (int r = 0; r < c->nranks; ++r) {
+            if (r == c->rank) { c->peer.mail[r] = c->mailbox; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, &host[rec * r], sizeof(h));
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; cudaGetLastError(); break; }
+            c->opened[r] = p;
+            c->peer.mail[r] = (double *)p;
+        }
+    }
+    // second round: did every rank manage to map every peer?
+    double *flag = (double *)dev;
+    double v = all_ok ? 0.0 : 1.0;
+    cudaMemcpy(flag, &v, sizeof(double), cudaMemcpyHostToDevice);
+    if (talk && n.AllReduce(flag, flag, 1, ncclFloat64, ncclSum, c->comm, nullptr) == ncclSuccess && cudaDeviceSynchronize() == cudaSuccess) {
+        cudaMemcpy(&v, flag, sizeof(double), cudaMemcpyDeviceToHost);
+        all_ok = all_ok && v == 0.0;
+    } else {
+        all_ok = false;
+    }
+    cudaFree(dev);
+    if (!all_ok) {
+        for (int r = 0; r < kMaxPeers; ++r) if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }
+        if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+        c->peer = PeerCtx{};
+        return false;
+    }
+    c->peer.nranks = c->nranks;
+    c->peer.rank = c->rank;
+    c->peer.seq = 0;
+    c->peer.extra[0] = c->peer.extra[1] = nullptr;
+    return true;
+}
+}  // namespace
 
 int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream) {
     if (!c || c->nranks == 1) return 0;
@@ -104,6 +184,11 @@ int lbfgsb200_comm_create(const char id[LBFGSB200_UNIQUE_ID_BYTES], int rank, in
         delete c;
         return LBFGSB200_ERR_NCCL;
     }
+    if (nranks > 1) {
+        const bool peers = lb::setup_peer_mailboxes(c);
+        if (getenv("LBFGSB200_DEBUG_TIMING") && rank == 0)
+            fprintf(stderr, "[lbfgsb200] scalar all-reduce transport: %s\n", peers ? "peer mailboxes (fused into the kernels)" : "ncclAllReduce");
+    }
     *out = reinterpret_cast<lbfgsb200_comm_t *>(c);
     return 0;
 }
@@ -112,6 +197,9 @@ void lbfgsb200_comm_destroy(lbfgsb200_comm_t *comm) {
     lb::Comm *c = reinterpret_cast<lb::Comm *>(comm);
     if (!c) return;
     lb::Nccl &n = lb::nccl();
+    for (int r = 0; r < lb::kMaxPeers; ++r)
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+    if (c->mailbox) cudaFree(c->mailbox);
     if (n.ok && c->comm) n.CommDestroy(c->comm);
     delete c;
 }

@@ -28,6 +28,14 @@ inline int grid_for(const Launch &L, int64_t n, int U) {
     if (tiles > L.max_grid) tiles = L.max_grid;
     return (int)tiles;
 }
+// The reduction workspace of one reducing launch: with peers, this launch gets the next exchange sequence number
+// (every rank issues the same launches in the same order, so the numbers agree).
+inline ReduceWs ws_for(const Launch &L) {
+    ReduceWs ws = L.ws;
+    if (ws.peer.nranks > 1 && L.peer_seq) ws.peer.seq = ++*L.peer_seq;
+    else ws.peer.nranks = 0;
+    return ws;
+}
 inline int threads_for(const Launch &L) { return L.sequential ? 1 : kThreads; }
 inline void count(const Launch &L) {
     if (L.launch_counter) ++*L.launch_counter;
@@ -493,11 +501,11 @@ void launch_dots(const Launch &L, const double *g, const double *d, const double
     const int grid = grid_for(L, n, kUt);
     count(L);
     if (d) {
-        LB_DISPATCH_S(L, (k_dots<true, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)),
-                      (k_dots<false, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)));
+        LB_DISPATCH_S(L, (k_dots<true, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, ws_for(L), out)),
+                      (k_dots<false, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, ws_for(L), out)));
     } else {
-        LB_DISPATCH_S(L, (k_dots<true, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)),
-                      (k_dots<false, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, L.ws, out)));
+        LB_DISPATCH_S(L, (k_dots<true, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, ws_for(L), out)),
+                      (k_dots<false, false><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, ws_for(L), out)));
     }
 }
 
@@ -507,20 +515,20 @@ void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g
     count(L);
     if (d) {
         LB_DISPATCH_S(L,
-                      (k_owl_pg<true, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
-                      (k_owl_pg<false, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
+                      (k_owl_pg<true, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, ws_for(L), out)),
+                      (k_owl_pg<false, true><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, ws_for(L), out)));
     } else {
         LB_DISPATCH_S(L,
-                      (k_owl_pg<true, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)),
-                      (k_owl_pg<false, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, L.ws, out)));
+                      (k_owl_pg<true, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, ws_for(L), out)),
+                      (k_owl_pg<false, false><<<grid, threads_for(L), 0, L.stream>>>({pg, x, g, d, c, start, end, goff}, n, ws_for(L), out)));
     }
 }
 
 void launch_init_dir(const Launch &L, double *d, const double *src, int64_t n, double *out) {
     const int grid = grid_for(L, n, kU);
     count(L);
-    LB_DISPATCH_S(L, (k_init_dir<true><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)),
-                  (k_init_dir<false><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_init_dir<true><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, ws_for(L), out)),
+                  (k_init_dir<false><<<grid, threads_for(L), 0, L.stream>>>({d, src}, n, ws_for(L), out)));
 }
 
 void launch_trial(const Launch &L, double *x, const double *xp, const double *d, double step, int64_t n,
@@ -548,7 +556,7 @@ static void history_impl(const Launch &L, const double *x, const double *xp, con
                          const double *pg, double *s, double *y, int64_t n, double nstep, bool damping, double *out,
                          int grid) {
 #define LB_HIST(D, O) \
-    k_history<S, D, O><<<grid, threads_for(L), 0, L.stream>>>({x, xp, g, gp, pg, s, y, nstep}, n, L.ws, out)
+    k_history<S, D, O><<<grid, threads_for(L), 0, L.stream>>>({x, xp, g, gp, pg, s, y, nstep}, n, ws_for(L), out)
     if (damping && pg) LB_HIST(true, true);
     else if (damping) LB_HIST(true, false);
     else if (pg) LB_HIST(false, true);
@@ -576,7 +584,7 @@ static void backward_impl(const Launch &L, bool first, bool last, double *q, con
                           const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
                           double *alpha_out, double *out, int grid) {
 #define LB_BWD(F, LA) \
-    k_backward<S, F, LA><<<grid, threads_for(L), 0, L.stream>>>({q, g, y, s_next, 0.0, gamma}, n, red_in, ys_j, alpha_out, L.ws, out)
+    k_backward<S, F, LA><<<grid, threads_for(L), 0, L.stream>>>({q, g, y, s_next, 0.0, gamma}, n, red_in, ys_j, alpha_out, ws_for(L), out)
     if (first && last) LB_BWD(true, true);
     else if (first) LB_BWD(true, false);
     else if (last) LB_BWD(false, true);
@@ -598,7 +606,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
                          int64_t n, const double *red_in, double ys_j, const double *alpha_in, int64_t start,
                          int64_t end, int64_t goff, double *out, int grid) {
 #define LB_FWD(LA, OW) \
-    k_forward<S, LA, OW><<<grid, threads_for(L), 0, L.stream>>>({r, s, aux, 0.0, start, end, goff}, n, red_in, ys_j, alpha_in, L.ws, out)
+    k_forward<S, LA, OW><<<grid, threads_for(L), 0, L.stream>>>({r, s, aux, 0.0, start, end, goff}, n, red_in, ys_j, alpha_in, ws_for(L), out)
     if (last && owl) LB_FWD(true, true);
     else if (last) LB_FWD(true, false);
     else LB_FWD(false, false);
@@ -619,8 +627,8 @@ void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t 
                           int64_t goff, double *out) {
     const int grid = grid_for(L, n, kU);
     count(L);
-    LB_DISPATCH_S(L, (k_owl_constrain<true><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)),
-                  (k_owl_constrain<false><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_owl_constrain<true><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, ws_for(L), out)),
+                  (k_owl_constrain<false><<<grid, threads_for(L), 0, L.stream>>>({d, pg, start, end, goff}, n, ws_for(L), out)));
 }
 
 template <int KIND>
@@ -640,8 +648,25 @@ void launch_vecdiff(const Launch &L, double *z, const double *x, const double *y
 void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n, double *out) {
     const int grid = grid_for(L, n, kU);
     count(L);
-    LB_DISPATCH_S(L, (k_dot<true><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)),
-                  (k_dot<false><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, L.ws, out)));
+    LB_DISPATCH_S(L, (k_dot<true><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, ws_for(L), out)),
+                  (k_dot<false><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, ws_for(L), out)));
+}
+
+__global__ void k_peer_allreduce(PeerCtx pc, double *buf, int count) {
+    __shared__ double tab[kMaxPeers + 1][kMailVals];
+    double vals[kMailVals];
+    if (threadIdx.x == 0)
+        for (int a = 0; a < count; ++a) vals[a] = buf[a];
+    peer_allreduce(pc, vals, count, tab);
+    if (threadIdx.x == 0)
+        for (int a = 0; a < count; ++a) buf[a] = vals[a];
+}
+void launch_peer_allreduce(const Launch &L, double *buf, int count) {
+    ReduceWs ws = L.ws;
+    if (ws.peer.nranks <= 1 || !L.peer_seq) return;
+    ws.peer.seq = ++*L.peer_seq;
+    if (L.launch_counter) ++*L.launch_counter;
+    k_peer_allreduce<<<1, 32, 0, L.stream>>>(ws.peer, buf, count);
 }
 
 }  // namespace lb

@@ -14,7 +14,8 @@ struct Launch {
     int max_grid = 148 * 8;   // CTAs: a multiple of the SM count (set from the device at create)
     bool streaming = true;    // evict-first loads/stores (vectors much larger than L2)
     bool sequential = false;  // reference-order reductions: every kernel runs as <<<1, 1>>> (validation only)
-    ReduceWs ws{};            // level-2 reduction workspace
+    ReduceWs ws{};            // level-2 reduction workspace (+ the peer mailboxes when sharded over GPUs)
+    unsigned long long *peer_seq = nullptr;   // the communicator's exchange counter (advanced per reducing launch)
     int64_t *launch_counter = nullptr;
 };
 
@@ -60,5 +61,8 @@ void launch_vecscale(const Launch &L, double *y, double c, int64_t n);
 void launch_veccpy(const Launch &L, double *y, const double *x, int64_t n, bool negate);
 void launch_vecdiff(const Launch &L, double *z, const double *x, const double *y, int64_t n);
 void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n, double *out);
+// multi-GPU: in-place sum of buf[0..count) (count <= kMailVals) over all ranks through the peer mailboxes, as a
+// stand-alone 1-warp kernel (for results that were not produced by one of the reducing kernels above)
+void launch_peer_allreduce(const Launch &L, double *buf, int count);
 
 }  // namespace lb

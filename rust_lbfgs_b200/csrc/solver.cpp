@@ -292,6 +292,10 @@ Launch Solver::launch_cfg() {
     L.streaming = streaming_;
     L.sequential = sequential_;
     L.ws = ws_;
+    if (const PeerCtx *pc = comm_peer(comm_)) {
+        L.ws.peer = *pc;
+        L.peer_seq = comm_peer_seq(comm_);
+    }
     L.launch_counter = &launch_counter_;
     return L;
 }
@@ -333,14 +337,20 @@ void Solver::profile_reset() {
 }
 
 // ---- scalar plumbing ------------------------------------------------------------------------
-int Solver::reduce_across_ranks(int s, int count) {
+int Solver::reduce_across_ranks(int s, int count, bool ours) {
     if (!comm_ || comm_size(comm_) == 1) return 0;
     prof_.allreduces += 1;
+    if (comm_peer(comm_)) {
+        if (ours) return 0;                       // summed over the ranks inside the producing kernel's epilogue
+        Launch L = launch_cfg();
+        launch_peer_allreduce(L, slot(s), count);  // e.g. a user objective's fused trial: 1-warp exchange kernel
+        return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+    }
     return comm_allreduce_sum(comm_, slot(s), count, stream_);
 }
 
-int Solver::fetch(int s, int count, double *host) {
-    int rc = reduce_across_ranks(s, count);
+int Solver::fetch(int s, int count, double *host, bool ours) {
+    int rc = reduce_across_ranks(s, count, ours);
     if (rc != 0) return fail(rc, "ncclAllReduce failed");
     cudaError_t e = cudaMemcpyAsync(scal_host_, slot(s), sizeof(double) * count, cudaMemcpyDeviceToHost, stream_);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H scalars)");
@@ -366,6 +376,13 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
     prof_end(LBFGSB200_K_EVALUATE, 0.0);
     const bool multi = comm_ && comm_size(comm_) > 1;
     if (erc != 0 && !multi) return false;
+    if (multi) {
+        post_eval_flag(erc);
+        // the objective's partial f (sl[0]) and the Err flag (sl[7]) ride along with the exchange that the
+        // following reducing kernel performs in its epilogue (peer mailboxes); with NCCL they are part of the slot
+        L.ws.peer.extra[0] = sl + 0;
+        L.ws.peer.extra[1] = sl + 7;
+    }
 
     // OWL-QN with gradient_only is the one combination that needs g.d next to the pseudo-gradient
     const bool want_gd = d_or_null != nullptr && (!owl_ || ls_.gradient_only);
@@ -378,20 +395,22 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
         launch_dots(L, g, want_gd ? d_or_null : nullptr, x, n_, sl + 1);
         prof_end(LBFGSB200_K_DOTS, (want_gd ? 3.0 : 2.0) * vbytes);
     }
-    return finish_eval(erc, false, dg_out);
+    return finish_eval(false, dg_out);
+}
+
+// An Err from evaluate on any rank must be seen by every rank (replicated control flow): the flag is summed
+// over the ranks with the dot products.
+void Solver::post_eval_flag(int erc) {
+    scal_host_[kMaxAcc] = erc != 0 ? 1.0 : 0.0;
+    cudaMemcpyAsync(slot(SLOT_EVAL) + 7, scal_host_ + kMaxAcc, sizeof(double), cudaMemcpyHostToDevice, stream_);
 }
 
 // The scalar half of an evaluation: (optional) cross-rank sum, D2H of the slot, the one host sync per trial.
-bool Solver::finish_eval(int erc, bool fused, double *dg_out) {
-    double *sl = slot(SLOT_EVAL);
+// `fused`: the slot was written by the objective's fused trial (not by one of our reducing kernels).
+bool Solver::finish_eval(bool fused, double *dg_out) {
     const bool multi = comm_ && comm_size(comm_) > 1;
-    if (multi) {  // an Err on any rank must be seen by every rank (replicated control flow)
-        const double flag = erc != 0 ? 1.0 : 0.0;
-        scal_host_[kMaxAcc] = flag;
-        cudaMemcpyAsync(sl + 7, scal_host_ + kMaxAcc, sizeof(double), cudaMemcpyHostToDevice, stream_);
-    }
     double h[kMaxAcc];
-    if (fetch(SLOT_EVAL, kMaxAcc, h) != 0) return false;
+    if (fetch(SLOT_EVAL, kMaxAcc, h, /*ours=*/!fused) != 0) return false;
     if (multi && h[7] != 0.0) return false;
 
     neval_ += 1;
@@ -422,7 +441,8 @@ bool Solver::trial_point(const double *xp, double stp, double *dg_out) {
         launch_counter_ += 1;
         const bool multi = comm_ && comm_size(comm_) > 1;
         if (erc != 0 && !multi) return false;
-        return finish_eval(erc, true, dg_out);
+        if (multi) post_eval_flag(erc);
+        return finish_eval(true, dg_out);
     }
     Launch L = launch_cfg();
     prof_begin(LBFGSB200_K_TRIAL);

@@ -24,6 +24,9 @@ struct Comm;
 int comm_rank(const Comm *c);
 int comm_size(const Comm *c);
 int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream);
+// peer-mailbox transport (nullptr: not available, the solver calls comm_allreduce_sum instead)
+const PeerCtx *comm_peer(const Comm *c);
+unsigned long long *comm_peer_seq(Comm *c);
 
 // Launch configuration for a device (SM count, L2 size, env overrides); shared by the solver,
 // the stand-alone primitives and the built-in objectives.
@@ -77,9 +80,11 @@ class Solver {
     int cuda_fail(cudaError_t e, const char *what);
     bool evaluate_point(const double *d_or_null, double *dg_out);  // evaluate + K2/K3 + allreduce + sync
     bool trial_point(const double *xp, double stp, double *dg_out); // K1 + evaluate_point, or the fused callback
-    bool finish_eval(int erc, bool fused, double *dg_out);         // allreduce + D2H + sync of SLOT_EVAL
-    int fetch(int s, int count, double *host);                     // allreduce + D2H + sync of a slot
-    int reduce_across_ranks(int s, int count);
+    bool finish_eval(bool fused, double *dg_out);                  // allreduce + D2H + sync of SLOT_EVAL
+    void post_eval_flag(int erc);
+    int fetch(int s, int count, double *host, bool ours = true);   // allreduce + D2H + sync of a slot
+    // ours = the slot was produced by one of our reducing kernels (already exchanged inside it with peer mailboxes)
+    int reduce_across_ranks(int s, int count, bool ours = true);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
     Launch launch_cfg();
 

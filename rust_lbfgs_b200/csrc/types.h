@@ -33,11 +33,30 @@ constexpr int kMinBlocks = LB_MINBLOCKS;  // resident CTAs per SM every kernel i
 constexpr int kU = LB_U;               // independent 128-bit loads per input vector per thread (tile = kU * 4 KB)
 constexpr int kMaxAcc = 8;             // accumulators per kernel (and doubles per scalar slot)
 
+// Cross-GPU exchange fused into the reducing kernels (one process per GPU, peers mapped with CUDA IPC over
+// NVLink / NVSwitch).  Every rank owns a mailbox ring in its HBM: entry (seq % kMailRing, sender) holds a sequence
+// word and up to kMailVals doubles.  The last CTA of a reducing kernel stores its totals into EVERY rank's
+// mailbox (peer stores), waits until all senders' entries for this seq have landed in its own mailbox, and sums
+// them in rank order — deterministic and bit-identical on every rank, which the replicated scalar control
+// logic needs.  No NCCL call, no extra launch.
+constexpr int kMaxPeers = 8;
+constexpr int kMailRing = 4;
+constexpr int kMailStride = 16;        // doubles per entry (128 B): [0] = seq word, [1..] = values
+constexpr int kMailVals = 12;
+struct PeerCtx {
+    int nranks;                    // 0 / 1 = no exchange
+    int rank;
+    unsigned long long seq;        // this launch's sequence number (same on every rank)
+    double *mail[kMaxPeers];       // mail[r]: rank r's mailbox as mapped into this process (mail[rank] is local)
+    double *extra[2];              // optional device scalars that ride along with the exchange (summed in place)
+};
+
 // Per-solver reduction workspace in HBM.
 struct ReduceWs {
     double *partials;      // [kMaxAcc][stride]
     unsigned int *ticket;  // zero between kernels
     int stride;            // >= max grid size
+    PeerCtx peer;          // multi-GPU: fused all-reduce of the results (nranks <= 1: none)
 };
 
 }  // namespace lb
