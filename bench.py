@@ -295,6 +295,7 @@ def run_ours(args):
                             if prof_all["ms"][k] > 0 and prof_all["bytes"][k] > 0},
         },
         "host_syncs": prof["host_syncs"], "allreduces": prof["allreduces"],
+        "allreduce_transport": comm.transport if comm is not None else None,
     }
     del x
     torch.cuda.empty_cache()

@@ -173,6 +173,10 @@ int  lbfgsb200_comm_unique_id(char id[LBFGSB200_UNIQUE_ID_BYTES]);
 int  lbfgsb200_comm_create(const char id[LBFGSB200_UNIQUE_ID_BYTES], int rank, int nranks, int device,
                            lbfgsb200_comm_t **out);
 void lbfgsb200_comm_destroy(lbfgsb200_comm_t *comm);
+/* How the solver sums its scalars over the ranks: 1 = peer mailboxes (CUDA IPC over NVLink; the exchange is fused
+ * into the reducing kernels' epilogue, no collective call), 0 = ncclAllReduce per step (fallback, or
+ * LBFGSB200_PEER_REDUCE=0). */
+int  lbfgsb200_comm_transport(const lbfgsb200_comm_t *comm);
 /* in-place sum of `count` doubles in device memory over all ranks (ncclAllReduce, ncclDouble, ncclSum) */
 int  lbfgsb200_comm_allreduce_sum(lbfgsb200_comm_t *comm, double *buf_dev, int count, void *stream);
 

@@ -107,6 +107,7 @@ def lib():
     _sig(L, "lbfgsb200_comm_unique_id", i32, [C.c_char_p])
     _sig(L, "lbfgsb200_comm_create", i32, [C.c_char_p, i32, i32, i32, pp(vp)])
     _sig(L, "lbfgsb200_comm_destroy", None, [vp])
+    _sig(L, "lbfgsb200_comm_transport", i32, [vp])
     _sig(L, "lbfgsb200_comm_allreduce_sum", i32, [vp, vp, i32, vp])
     _sig(L, "lbfgsb200_create", i32, [pp(Param), i64, i64, i64, i32, vp, vp, pp(vp)])
     _sig(L, "lbfgsb200_destroy", None, [vp])

@@ -193,6 +193,10 @@ int lbfgsb200_comm_create(const char id[LBFGSB200_UNIQUE_ID_BYTES], int rank, in
     return 0;
 }
 
+int lbfgsb200_comm_transport(const lbfgsb200_comm_t *comm) {
+    return lb::comm_peer(reinterpret_cast<const lb::Comm *>(comm)) ? 1 : 0;
+}
+
 void lbfgsb200_comm_destroy(lbfgsb200_comm_t *comm) {
     lb::Comm *c = reinterpret_cast<lb::Comm *>(comm);
     if (!c) return;

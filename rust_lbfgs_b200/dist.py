@@ -96,6 +96,11 @@ class Comm:
             raise RuntimeError(f"lbfgsb200_comm_create failed: {_lib.STATUS_NAMES.get(st, st)}")
         self._handle = out
 
+    @property
+    def transport(self):
+        """"peer_mailboxes" (exchange fused into the kernels over NVLink peer stores) or "nccl_allreduce"."""
+        return "peer_mailboxes" if _lib.lib().lbfgsb200_comm_transport(self._handle) == 1 else "nccl_allreduce"
+
     def allreduce_sum_(self, tensor):
         import torch
         st = _lib.lib().lbfgsb200_comm_allreduce_sum(self._handle, tensor.data_ptr(), tensor.numel(),

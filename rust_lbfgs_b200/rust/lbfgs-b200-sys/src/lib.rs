@@ -115,6 +115,7 @@ extern "C" {
     pub fn lbfgsb200_comm_unique_id(id: *mut c_char) -> c_int;
     pub fn lbfgsb200_comm_create(id: *const c_char, rank: c_int, nranks: c_int, device: c_int, out: *mut *mut lbfgsb200_comm_t) -> c_int;
     pub fn lbfgsb200_comm_destroy(comm: *mut lbfgsb200_comm_t);
+    pub fn lbfgsb200_comm_transport(comm: *const lbfgsb200_comm_t) -> c_int;
     pub fn lbfgsb200_comm_allreduce_sum(comm: *mut lbfgsb200_comm_t, buf_dev: *mut f64, count: c_int, stream: *mut c_void) -> c_int;
 
     pub fn lbfgsb200_create(param: *const lbfgsb200_param_t, n_local: i64, n_global: i64, global_offset: i64, device: c_int,
