@@ -374,8 +374,8 @@ def main():
     ap.add_argument("--n", "--elems", dest="n", type=float, default=1e8, help="elements per GPU")
     ap.add_argument("--m", "--history", dest="m", type=int, default=6)
     ap.add_argument("--ref-n", type=float, default=5e6, help="--impl reference: sample size")
-    ap.add_argument("--cpu-n", type=float, default=1e7, help="cpu_baseline sample size")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-n", type=float, default=2e7, help="cpu_baseline sample size")
+    ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused-trial", action="store_true",
                     help="line-search trials as K1 + evaluate + K2 (three passes) instead of the fused one-pass trial")

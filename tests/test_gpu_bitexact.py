@@ -126,6 +126,35 @@ def test_lj38_bit_exact(oracle, golden_dir):
         assert_bit_identical(ref, got, f"lj38 {kw}")
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_problems_bit_exact(oracle, seed):
+    """Random starts, sizes and option mixes (line search x damping x OWL-QN range x history depth)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([6, 50, 128, 514, 1502]))
+    x0 = rosenbrock_x0(n) * (1.0 + 0.3 * rng.standard_normal(n))
+    algo = int(rng.integers(0, 4))
+    name = ["MoreThuente", "BacktrackingArmijo", "BacktrackingWolfe", "BacktrackingStrongWolfe"][algo]
+    m = int(rng.choice([1, 2, 5, 6, 9]))
+    kw = dict(ls_algorithm=algo, m=m, max_iterations=45)
+    b = seq().with_linesearch_algorithm(name).with_m(m).with_max_iterations(45)
+    if rng.random() < 0.4 and algo != 0:
+        kw["damping"] = 1
+        b = b.with_damping(True)
+    if rng.random() < 0.5:
+        c = float(rng.uniform(0.1, 3.0))
+        start = int(rng.integers(0, n // 2))
+        end = int(rng.integers(start + 1, n + 1))
+        kw.update(orthantwise=1, owl_c=c, owl_start=start, owl_end=end)
+        b = b.with_orthantwise(c, start, end)
+    if rng.random() < 0.3:
+        ms = float(rng.choice([0.05, 0.5, 10.0]))
+        kw["max_step_size"] = ms
+        b = b.with_max_step_size(ms)
+    ref = oracle_run(oracle, x0, "rosenbrock", **kw)
+    got = gpu_minimize(b, x0, R.Rosenbrock())
+    assert_bit_identical(ref, got, f"seed {seed}: n={n} {kw}")
+
+
 def test_error_status_bit_exact(oracle):
     """Failure paths end with the same status after the same number of iterations (src/line.rs:213-220)."""
     for kw, b in ((dict(ls_max_linesearch=1), seq().with_max_linesearch(1)),
