@@ -294,6 +294,15 @@ void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective);
 /* LBFGSB200_REDUCE_* for the objective's own sum (f); SEQUENTIAL is implemented for Rosenbrock, Booth and
  * Lennard-Jones (exp/log in the GLMs are not bit-reproducible against a CPU libm anyway) */
 int  lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int reduction);
+/* Multi-GPU objectives.  Rosenbrock is shard-local (no-op).
+ *   GLM: this rank's X / y hold a block of ROWS; w is replicated on every rank and the solver runs unsharded
+ *        (comm = NULL in lbfgsb200_create): eval all-reduces f and the ncol-vector gradient, so every rank sees the
+ *        same bits.  shard_offsets is ignored.
+ *   Lennard-Jones: the solver shards the 3N coordinates (lbfgsb200_create with comm); shard_offsets[0..nranks] are
+ *        the element offsets of every rank's shard (multiples of 3): eval gathers all positions over NVLink and
+ *        computes this rank's forces against all atoms (same bits as on one GPU) and its partial energy.
+ * comm = NULL resets to single-GPU behaviour. */
+int  lbfgsb200_objective_set_shard(lbfgsb200_objective_t *objective, lbfgsb200_comm_t *comm, const int64_t *shard_offsets);
 /* the lbfgsb200_eval_fn for every built-in objective: pass the objective handle as `user` */
 int  lbfgsb200_objective_eval(void *objective, const double *x_dev, double *g_dev, int64_t n_local,
                               void *stream, double *fx_dev);

@@ -42,6 +42,9 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -61,6 +64,9 @@ Nccl &nccl() {
         n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
         n.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
         n.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllGather");
+        n.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclBroadcast");
+        n.GroupStart = (int (*)())dlsym(n.handle, "ncclGroupStart");
+        n.GroupEnd = (int (*)())dlsym(n.handle, "ncclGroupEnd");
         n.GetErrorString = (const char *(*)(int))dlsym(n.handle, "ncclGetErrorString");
         n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce;
     });
@@ -151,6 +157,24 @@ int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream)
     if (!n.ok) return LBFGSB200_ERR_NCCL;
     int rc = n.AllReduce(buf_dev, buf_dev, (size_t)count, ncclFloat64, ncclSum, c->comm, stream);
     return rc == ncclSuccess ? 0 : LBFGSB200_ERR_NCCL;
+}
+
+// All-gather of contiguous shards of unequal length: rank r's `send` (offsets[r+1] - offsets[r] doubles) lands at
+// recv_all + offsets[r] on every rank (one grouped ncclBroadcast per rank over NVLink).
+int comm_allgatherv(Comm *c, const double *send, double *recv_all, const int64_t *offsets, cudaStream_t stream) {
+    if (!c || c->nranks == 1) return 0;
+    Nccl &n = nccl();
+    if (!n.ok || !n.Broadcast || !n.GroupStart || !n.GroupEnd) return LBFGSB200_ERR_NCCL;
+    if (n.GroupStart() != ncclSuccess) return LBFGSB200_ERR_NCCL;
+    int bad = 0;
+    for (int r = 0; r < c->nranks; ++r) {
+        const size_t cnt = (size_t)(offsets[r + 1] - offsets[r]);
+        double *dst = recv_all + offsets[r];
+        const void *src = (r == c->rank) ? (const void *)send : (const void *)dst;
+        if (n.Broadcast(src, dst, cnt, ncclFloat64, r, c->comm, stream) != ncclSuccess) bad = 1;
+    }
+    if (n.GroupEnd() != ncclSuccess || bad) return LBFGSB200_ERR_NCCL;
+    return 0;
 }
 
 }  // namespace lb

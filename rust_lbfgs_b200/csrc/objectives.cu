@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "../../include/lbfgsb200.h"
 #include "reduce.cuh"
@@ -38,6 +39,10 @@ struct Objective {
     bool fused = true;           // LBFGSB200_GLM_FUSED=0 forces the two-pass kernels
     // LJ
     double eps = 1.0, sigma = 1.0;
+    // multi-GPU (lbfgsb200_objective_set_shard)
+    Comm *comm = nullptr;            // GLM: rows of X sharded, f and g summed over ranks; LJ: atoms sharded
+    std::vector<int64_t> offsets;    // LJ: element offsets of every rank's shard (nranks + 1)
+    double *xall = nullptr;          // LJ: all positions, gathered before every evaluation
 };
 
 // ---- Rosenbrock ------------------------------------------------------------------------------
@@ -365,11 +370,15 @@ int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, dou
 // row i, then pairs (i', i) for i' > i), and (p_i - p_j) == -(p_j - p_i) exactly, so a sequential
 // ascending loop over all partners reproduces forces[i] bit for bit.
 constexpr int kLjTile = 256;
+// Sharded over GPUs: x holds ALL natoms positions (gathered), this rank owns atoms [a0, a0 + nloc) and writes
+// their gradient to g[0 .. 3 nloc); partners are still visited in ascending global order, so the forces are the
+// same bits as on one GPU.
 __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
-                                                double eps, double sigma, ReduceWs ws, double *fx) {
+                                                int64_t a0, int64_t nloc, double eps, double sigma, ReduceWs ws, double *fx) {
     __shared__ double sp[kLjTile * 3];
-    const int64_t i = (int64_t)blockIdx.x * kLjTile + threadIdx.x;
-    const bool active = i < natoms;
+    const int64_t il = (int64_t)blockIdx.x * kLjTile + threadIdx.x;
+    const int64_t i = a0 + il;
+    const bool active = il < nloc;
     double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
     if (active) { pi0 = x[3 * i]; pi1 = x[3 * i + 1]; pi2 = x[3 * i + 2]; }
     double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
@@ -396,12 +405,71 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
         }
     }
     if (active) {  // gx = -forces, lj.rs:116
-        g[3 * i] = -f0;
-        g[3 * i + 1] = -f1;
-        g[3 * i + 2] = -f2;
+        g[3 * il] = -f0;
+        g[3 * il + 1] = -f1;
+        g[3 * il + 2] = -f2;
     }
     double acc[1] = {e};
     grid_reduce<1>(acc, ws, fx);
+}
+
+// Sharded over GPUs a rank owns only N/P atoms — too few threads for one thread per atom — so P lanes of a warp
+// share an atom: lane `sub` visits partners sub, sub + P, ... of every tile (ascending), and the P partial forces
+// are combined with a fixed xor-butterfly.  Deterministic, but the association differs from the one-thread
+// order, so forces agree with the one-GPU kernel to rounding (1e-16 relative), not bit for bit.
+template <int P>
+__global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
+                                                      int64_t a0, int64_t nloc, double eps, double sigma, ReduceWs ws,
+                                                      double *fx) {
+    __shared__ double sp[kLjTile * 3];
+    constexpr int kAtoms = kLjTile / P;
+    const int sub = threadIdx.x % P;
+    const int64_t il = (int64_t)blockIdx.x * kAtoms + threadIdx.x / P;
+    const int64_t i = a0 + il;
+    const bool active = il < nloc;
+    double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
+    if (active) { pi0 = x[3 * i]; pi1 = x[3 * i + 1]; pi2 = x[3 * i + 2]; }
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
+    for (int64_t base = 0; base < natoms; base += kLjTile) {
+        const int64_t cnt = (natoms - base < kLjTile) ? (natoms - base) : kLjTile;
+        __syncthreads();
+        for (int64_t q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * base + q];
+        __syncthreads();
+        if (!active) continue;
+        for (int jj = sub; jj < (int)cnt; jj += P) {
+            const int64_t j = base + jj;
+            if (j == i) continue;
+            const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
+            const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const double qq = sigma / r;
+            const double q2 = qq * qq;
+            const double s6 = q2 * (q2 * q2);
+            if (j < i) e += 4.0 * eps * (s6 * s6 - s6);
+            const double gr = 24.0 * eps * (s6 - 2.0 * (s6 * s6)) / r;
+            f0 += gr * (-d0) / r;
+            f1 += gr * (-d1) / r;
+            f2 += gr * (-d2) / r;
+        }
+    }
+#pragma unroll
+    for (int off = P / 2; off > 0; off >>= 1) {
+        f0 += __shfl_xor_sync(0xffffffffu, f0, off);
+        f1 += __shfl_xor_sync(0xffffffffu, f1, off);
+        f2 += __shfl_xor_sync(0xffffffffu, f2, off);
+    }
+    if (active && sub == 0) {
+        g[3 * il] = -f0;
+        g[3 * il + 1] = -f1;
+        g[3 * il + 2] = -f2;
+    }
+    double acc[1] = {e};
+    grid_reduce<1>(acc, ws, fx);
+}
+
+template <int P>
+void launch_lj_split(Objective *o, double *g, int64_t natoms, int64_t a0, int64_t nloc, cudaStream_t stream, double *fx) {
+    const int64_t blocks = (nloc + kLjTile / P - 1) / (kLjTile / P);
+    k_lj_split<P><<<(int)blocks, kLjTile, 0, stream>>>(o->xall, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx);
 }
 
 // Reference-order energy (LBFGSB200_REDUCE_SEQUENTIAL): one thread walks the pairs (i, j < i) exactly as
@@ -480,15 +548,42 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
         }
         case OBJ_LJ: {
             if (n % 3 != 0 || n < 3) return LBFGSB200_ERR_INVALID_PARAM;
-            const int64_t na = n / 3;
-            const int64_t blocks = (na + kLjTile - 1) / kLjTile;
+            const int64_t nloc = n / 3;
+            const int64_t blocks = (nloc + kLjTile - 1) / kLjTile;
             if (blocks > o->ws.stride) return LBFGSB200_ERR_INVALID_PARAM;
-            k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, na, o->eps, o->sigma, o->ws, fx);
-            if (o->sequential) k_lj_energy_seq<<<1, 1, 0, stream>>>(x, na, o->eps, o->sigma, fx);
+            if (o->comm && comm_size(o->comm) > 1) {  // atoms sharded: gather all positions, forces stay local
+                const int r = comm_rank(o->comm);
+                if (o->offsets[r + 1] - o->offsets[r] != n) return LBFGSB200_ERR_INVALID_PARAM;
+                const int grc = comm_allgatherv(o->comm, x, o->xall, o->offsets.data(), stream);
+                if (grc != 0) return grc;
+                // lanes per atom: enough threads to fill the GPU (~4 CTAs of 256 per SM), capped by the workspace
+                const int64_t natoms = o->offsets.back() / 3, a0 = o->offsets[r] / 3;
+                const int64_t want = (int64_t)o->dev.sm_count * 4 * kLjTile;
+                int P = 1;
+                while (P < 32 && nloc * P < want && (nloc * 2 * P + kLjTile - 1) / kLjTile <= o->ws.stride) P *= 2;
+                switch (P) {
+                    case 1: k_lj<<<(int)blocks, kLjTile, 0, stream>>>(o->xall, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx); break;
+                    case 2: launch_lj_split<2>(o, g, natoms, a0, nloc, stream, fx); break;
+                    case 4: launch_lj_split<4>(o, g, natoms, a0, nloc, stream, fx); break;
+                    case 8: launch_lj_split<8>(o, g, natoms, a0, nloc, stream, fx); break;
+                    case 16: launch_lj_split<16>(o, g, natoms, a0, nloc, stream, fx); break;
+                    default: launch_lj_split<32>(o, g, natoms, a0, nloc, stream, fx); break;
+                }
+                break;
+            }
+            k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, nloc, 0, nloc, o->eps, o->sigma, o->ws, fx);
+            if (o->sequential) k_lj_energy_seq<<<1, 1, 0, stream>>>(x, nloc, o->eps, o->sigma, fx);
             break;
         }
         default:
             return LBFGSB200_ERR_INVALID_PARAM;
+    }
+    if (o->kind == OBJ_GLM && o->comm && comm_size(o->comm) > 1) {
+        // rows of X are sharded over the ranks, w is replicated: every rank needs the full f and gradient
+        // (ncclAllReduce returns the same bits on every rank, so the replicated solvers stay in lockstep)
+        int arc = comm_allreduce_sum(o->comm, g, (int)o->ncol, stream);
+        if (arc == 0) arc = comm_allreduce_sum(o->comm, fx, 1, stream);
+        if (arc != 0) return arc;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
@@ -563,6 +658,26 @@ int lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int redu
     o->sequential = reduction == LBFGSB200_REDUCE_SEQUENTIAL;
     return 0;
 }
+int lbfgsb200_objective_set_shard(lbfgsb200_objective_t *objective, lbfgsb200_comm_t *comm, const int64_t *shard_offsets) {
+    lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
+    if (!o) return LBFGSB200_ERR_INVALID_PARAM;
+    lb::Comm *c = reinterpret_cast<lb::Comm *>(comm);
+    if (o->xall) { cudaFree(o->xall); o->xall = nullptr; }
+    o->offsets.clear();
+    o->comm = nullptr;
+    if (!c || lb::comm_size(c) == 1) return 0;
+    if (o->kind == lb::OBJ_LJ) {
+        if (!shard_offsets) return LBFGSB200_ERR_INVALID_PARAM;
+        const int nr = lb::comm_size(c);
+        o->offsets.assign(shard_offsets, shard_offsets + nr + 1);
+        for (int r = 0; r <= nr; ++r)
+            if (o->offsets[r] % 3 != 0 || (r > 0 && o->offsets[r] < o->offsets[r - 1])) return LBFGSB200_ERR_INVALID_PARAM;
+        if (cudaSetDevice(o->dev.device) != cudaSuccess ||
+            cudaMalloc((void **)&o->xall, sizeof(double) * (size_t)o->offsets.back()) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    }
+    o->comm = c;   // Rosenbrock / Booth are shard-local: nothing to exchange
+    return 0;
+}
 int lbfgsb200_objective_has_trial_eval(const lbfgsb200_objective_t *objective) {
     const lb::Objective *o = reinterpret_cast<const lb::Objective *>(objective);
     return (o && o->kind == lb::OBJ_ROSENBROCK) ? 1 : 0;
@@ -579,6 +694,7 @@ void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
     if (o->t) cudaFree(o->t);
     if (o->gpart) cudaFree(o->gpart);
     if (o->gfused) cudaFree(o->gfused);
+    if (o->xall) cudaFree(o->xall);
     lb::free_reduce_ws(&o->ws);
     delete o;
 }

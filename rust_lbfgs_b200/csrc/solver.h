@@ -24,6 +24,7 @@ struct Comm;
 int comm_rank(const Comm *c);
 int comm_size(const Comm *c);
 int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream);
+int comm_allgatherv(Comm *c, const double *send, double *recv_all, const int64_t *offsets, cudaStream_t stream);
 // peer-mailbox transport (nullptr: not available, the solver calls comm_allreduce_sum instead)
 const PeerCtx *comm_peer(const Comm *c);
 unsigned long long *comm_peer_seq(Comm *c);

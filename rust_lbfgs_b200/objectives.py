@@ -11,6 +11,26 @@ from . import _lib
 class _Builtin:
     def __init__(self):
         self._handles = {}
+        self._shard = None   # (comm, offsets or None)
+
+    def shard(self, comm, offsets=None):
+        """Multi-GPU: see lbfgsb200_objective_set_shard.  GLM: rows of X are sharded (offsets unused);
+        LennardJones: offsets = element offsets of every rank's shard (len world + 1, multiples of 3)."""
+        self._shard = (comm, None if offsets is None else [int(o) for o in offsets])
+        for device, h in self._handles.items():
+            self._apply_shard(h)
+        return self
+
+    def _apply_shard(self, handle):
+        if self._shard is None:
+            return
+        comm, offsets = self._shard
+        arr = None
+        if offsets is not None:
+            arr = (C.c_int64 * len(offsets))(*offsets)
+        st = _lib.lib().lbfgsb200_objective_set_shard(handle, comm._handle, arr)
+        if st != 0:
+            raise RuntimeError(f"lbfgsb200_objective_set_shard failed: {_lib.STATUS_NAMES.get(st, st)}")
 
     def _create(self, L, device, out):
         raise NotImplementedError
@@ -38,6 +58,7 @@ class _Builtin:
             if st != 0:
                 raise RuntimeError(f"creating objective failed: {_lib.STATUS_NAMES.get(st, st)}")
             self._handles[device] = out
+            self._apply_shard(out)
         return self._handles[device]
 
     def close(self):

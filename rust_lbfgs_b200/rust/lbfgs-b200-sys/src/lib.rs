@@ -166,6 +166,7 @@ extern "C" {
                                    out: *mut *mut lbfgsb200_objective_t) -> c_int;
     pub fn lbfgsb200_objective_lennard_jones(device: c_int, epsilon: f64, sigma: f64, out: *mut *mut lbfgsb200_objective_t) -> c_int;
     pub fn lbfgsb200_objective_set_reduction(objective: *mut lbfgsb200_objective_t, reduction: c_int) -> c_int;
+    pub fn lbfgsb200_objective_set_shard(objective: *mut lbfgsb200_objective_t, comm: *mut lbfgsb200_comm_t, shard_offsets: *const i64) -> c_int;
     pub fn lbfgsb200_objective_destroy(objective: *mut lbfgsb200_objective_t);
     pub fn lbfgsb200_objective_eval(objective: *mut c_void, x_dev: *const f64, g_dev: *mut f64, n_local: i64, stream: *mut c_void,
                                     fx_dev: *mut f64) -> c_int;

@@ -17,7 +17,18 @@ import torch
 
 import rust_lbfgs_b200 as R
 
-DEV = torch.device("cuda", 0)
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(LOCAL)
+DEV = torch.device("cuda", LOCAL)
+COMM = None
+if WORLD > 1:   # torchrun: one process per GPU; GLM rows / LJ atoms are sharded over the ranks
+    import torch.distributed as dist
+    from rust_lbfgs_b200 import dist as D
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=DEV)
+    COMM = D.Comm(RANK, WORLD, LOCAL)
 
 
 def sync_time():
@@ -40,7 +51,9 @@ def solve(builder, x, obj, tag, extra=None, max_iter=None):
                evaluations=rep.neval, fx=rep.fx, gnorm=rep.gnorm,
                it_per_s=(len(ncalls) - 1) / (t1 - t0), ms_per_evaluation=1e3 * (t1 - t0) / max(1, rep.neval))
     rec.update(extra or {})
-    print(json.dumps(rec), flush=True)
+    rec["n_gpus"] = WORLD
+    if RANK == 0:
+        print(json.dumps(rec), flush=True)
     return rec
 
 
@@ -63,13 +76,15 @@ def small_n():
 def make_glm(nrow, ncol, seed=2024):
     """X: column 0 = 1, others N(0,1); w* 1% non-zeros; y ~ Bernoulli(sigmoid(X w*)).  Generated on the device in
     row chunks (80 GB at the full size)."""
+    g0 = torch.Generator(device=DEV)
+    g0.manual_seed(2024)            # the true model is the same on every rank ...
     g = torch.Generator(device=DEV)
-    g.manual_seed(seed)
+    g.manual_seed(seed)             # ... the rows are this rank's own
     X = torch.empty((nrow, ncol), dtype=torch.float64, device=DEV)
     wstar = torch.zeros(ncol, dtype=torch.float64, device=DEV)
     nz = max(1, ncol // 100)
-    idx = torch.randperm(ncol, generator=g, device=DEV)[:nz]
-    wstar[idx] = torch.randn(nz, generator=g, device=DEV, dtype=torch.float64)
+    idx = torch.randperm(ncol, generator=g0, device=DEV)[:nz]
+    wstar[idx] = torch.randn(nz, generator=g0, device=DEV, dtype=torch.float64)
     y = torch.empty(nrow, dtype=torch.float64, device=DEV)
     chunk = max(1, min(nrow, (1 << 28) // ncol))
     for r0 in range(0, nrow, chunk):
@@ -83,9 +98,12 @@ def make_glm(nrow, ncol, seed=2024):
 
 def cfg3(full):
     """OWL-QN L1-regularised logistic regression, intercept unpenalised (start = 1), mirrors tests/owlqn.rs:46-49."""
-    nrow, ncol = (1_000_000, 10_000) if full else (100_000, 2_000)
-    X, y = make_glm(nrow, ncol)
+    nrow_all, ncol = (1_000_000, 10_000) if full else (100_000, 2_000)
+    nrow = nrow_all // WORLD          # this rank's block of rows (w is replicated, the solver runs unsharded)
+    X, y = make_glm(nrow, ncol, seed=3000 + RANK)
     obj = R.Glm("logistic", X, y)
+    if COMM is not None:
+        obj.shard(COMM)
     w = torch.zeros(ncol, dtype=torch.float64, device=DEV)
     gx = torch.empty_like(w)
     # objective alone
@@ -94,19 +112,22 @@ def cfg3(full):
     fx = torch.zeros(1, dtype=torch.float64, device=DEV)
     st = int(torch.cuda.current_stream().cuda_stream)
     for _ in range(2):
-        L.lbfgsb200_objective_eval(obj._user_ptr(0), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
+        L.lbfgsb200_objective_eval(obj._user_ptr(LOCAL), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
     t0 = sync_time()
     reps = 5
     for _ in range(reps):
-        L.lbfgsb200_objective_eval(obj._user_ptr(0), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
+        L.lbfgsb200_objective_eval(obj._user_ptr(LOCAL), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
     t1 = sync_time()
     xbytes = 8.0 * nrow * ncol
-    print(json.dumps(dict(config=f"cfg3 glm objective alone {nrow}x{ncol}", ms_per_evaluation=1e3 * (t1 - t0) / reps,
-                          X_GB=xbytes / 1e9, GBps_one_pass_equivalent=xbytes / 1e9 / ((t1 - t0) / reps))), flush=True)
-    c = 1.0 * nrow / 500.0   # tests/owlqn.rs uses c = 1 with 500 rows
-    solve(R.lbfgs().with_orthantwise(c, 1).with_epsilon(1e-4), w, obj, f"cfg3 owlqn logistic {nrow}x{ncol} c={c}",
-          extra=dict(X_GB=xbytes / 1e9), max_iter=60)
-    print(json.dumps(dict(config="cfg3 sparsity", nonzeros=int((w != 0).sum()), ncol=ncol)), flush=True)
+    if RANK == 0:
+        print(json.dumps(dict(config=f"cfg3 glm objective alone {nrow_all}x{ncol} over {WORLD} GPU(s)",
+                              ms_per_evaluation=1e3 * (t1 - t0) / reps, X_GB_per_gpu=xbytes / 1e9,
+                              GBps_per_gpu_one_pass_equivalent=xbytes / 1e9 / ((t1 - t0) / reps))), flush=True)
+    c = 1.0 * nrow_all / 500.0   # tests/owlqn.rs uses c = 1 with 500 rows
+    solve(R.lbfgs().with_orthantwise(c, 1).with_epsilon(1e-4), w, obj, f"cfg3 owlqn logistic {nrow_all}x{ncol} c={c}",
+          extra=dict(X_GB_per_gpu=xbytes / 1e9), max_iter=60)
+    if RANK == 0:
+        print(json.dumps(dict(config="cfg3 sparsity", nonzeros=int((w != 0).sum()), ncol=ncol)), flush=True)
 
 
 def cfg4(full):
@@ -117,10 +138,18 @@ def cfg4(full):
     p = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
     p += rng.uniform(-0.05, 0.05, p.shape)
     na = p.shape[0]
-    for tag, b in (("gradient-only max_linesearch=2", R.lbfgs().with_gradient_only().with_max_linesearch(2)),
-                   ("damped", R.lbfgs().with_damping(True))):
-        x = torch.tensor(p.ravel(), dtype=torch.float64, device=DEV)
-        solve(b, x, R.LennardJones(), f"cfg4 lj {na} atoms {tag}", extra=dict(pairs=na * (na - 1) // 2),
+    flat = p.ravel()
+    for tag, mk in (("gradient-only max_linesearch=2", lambda: R.lbfgs().with_gradient_only().with_max_linesearch(2)),
+                    ("damped", lambda: R.lbfgs().with_damping(True))):
+        b, lj = mk(), R.LennardJones()
+        if COMM is not None:   # atoms sharded: solver vectors and forces local, positions gathered per evaluation
+            offs = [D.shard_range(flat.size, r, WORLD, granule=6)[0] for r in range(WORLD)] + [flat.size]
+            lj.shard(COMM, offs)
+            b = b.with_shard(COMM, flat.size, offs[RANK])
+            x = torch.tensor(flat[offs[RANK]:offs[RANK + 1]], dtype=torch.float64, device=DEV)
+        else:
+            x = torch.tensor(flat, dtype=torch.float64, device=DEV)
+        solve(b, x, lj, f"cfg4 lj {na} atoms {tag}", extra=dict(pairs=na * (na - 1) // 2),
               max_iter=21 if full else 41)
 
 
@@ -130,11 +159,14 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="cfg1,small,cfg3,cfg4")
     a = ap.parse_args()
     which = a.only.split(",")
-    if "cfg1" in which:
+    if "cfg1" in which and WORLD == 1:
         cfg1()
-    if "small" in which:
+    if "small" in which and WORLD == 1:
         small_n()
     if "cfg4" in which:
         cfg4(a.full)
     if "cfg3" in which:
         cfg3(a.full)
+    if COMM is not None:
+        COMM.close()
+        dist.destroy_process_group()

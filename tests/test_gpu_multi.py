@@ -113,3 +113,112 @@ def test_two_gpus_match_one_gpu():
         if len(trace) == len(a["trace"]) and len(trace) <= 45:
             x1 = x.cpu().numpy()
             assert np.max(np.abs(x1 - xs)) <= 1e-8 * np.max(np.abs(x1)), case
+
+
+# ---- sharded objectives: GLM by rows (solver replicated), Lennard-Jones by atoms (solver sharded) --------------------
+def _glm_data(nrow=6000, ncol=200, seed=4):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((nrow, ncol))
+    X[:, 0] = 1.0
+    wt = np.zeros(ncol)
+    wt[rng.choice(ncol, 8, replace=False)] = rng.standard_normal(8)
+    y = (rng.random(nrow) < 1 / (1 + np.exp(-(X @ wt)))).astype(np.float64)
+    return X, y
+
+
+def _lj_positions(side=7, seed=7):
+    rng = np.random.default_rng(seed)
+    g = np.arange(side, dtype=np.float64) * 1.12
+    p = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    return (p + rng.uniform(-0.05, 0.05, p.shape)).ravel()
+
+
+def _worker_objectives(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import rust_lbfgs_b200 as R
+    from rust_lbfgs_b200 import dist as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    comm = D.Comm(rank, world, rank)
+    out = {}
+    try:
+        # GLM: rows sharded, w replicated, solver unsharded
+        X, y = _glm_data()
+        r0, r1 = rank * len(y) // world, (rank + 1) * len(y) // world
+        obj = R.Glm("logistic", torch.tensor(X[r0:r1], device=dev), torch.tensor(y[r0:r1], device=dev)).shard(comm)
+        w = torch.zeros(X.shape[1], dtype=torch.float64, device=dev)
+        tr = []
+        rep = R.lbfgs().with_orthantwise(20.0, 1).with_max_iterations(40).minimize(
+            w, obj, lambda p: tr.append((p.niter, p.neval, p.ncall, p.fx)) and False)
+        out["glm"] = dict(status=rep.status_name, trace=tr, w=w.cpu().numpy())
+        # LJ: atoms sharded (granule 6 keeps shard boundaries on atoms and even)
+        p0 = _lj_positions()
+        n = p0.size
+        offs = [D.shard_range(n, r, world, granule=6)[0] for r in range(world)] + [n]
+        lo, hi = offs[rank], offs[rank + 1]
+        lj = R.LennardJones().shard(comm, offs)
+        x = torch.tensor(p0[lo:hi], device=dev)
+        tr = []
+        rep = R.lbfgs().with_shard(comm, n, lo).with_max_iterations(25).minimize(
+            x, lj, lambda p: tr.append((p.niter, p.neval, p.ncall, p.fx, p.gnorm)) and False)
+        out["lj"] = dict(status=rep.status_name, trace=tr, x=x.cpu().numpy(), lo=lo, hi=hi)
+        q.put((rank, out))
+    finally:
+        comm.close()
+        dist.destroy_process_group()
+
+
+def test_two_gpus_sharded_glm_and_lj():
+    import torch
+    import torch.multiprocessing as mp
+    import rust_lbfgs_b200 as R
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_objectives, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+
+    # GLM: both ranks ran the same replicated solve on bit-identical f / g
+    a, c = res[0]["glm"], res[1]["glm"]
+    assert a["status"] == c["status"] and a["trace"] == c["trace"] and np.array_equal(a["w"], c["w"])
+    X, y = _glm_data()
+    w = torch.zeros(X.shape[1], dtype=torch.float64, device="cuda:0")
+    tr = []
+    rep = R.lbfgs().with_orthantwise(20.0, 1).with_max_iterations(40).minimize(
+        w, R.Glm("logistic", torch.tensor(X, device="cuda:0"), torch.tensor(y, device="cuda:0")),
+        lambda p: tr.append((p.niter, p.neval, p.ncall, p.fx)) and False)
+    k = min(10, len(tr), len(a["trace"]))
+    assert [t[:3] for t in tr[:k]] == [t[:3] for t in a["trace"][:k]]
+    for s, t in zip(tr[:k], a["trace"][:k]):
+        assert abs(s[3] - t[3]) <= 1e-11 * abs(s[3])
+    assert abs(tr[-1][3] - a["trace"][-1][3]) <= 1e-6 * abs(tr[-1][3])
+    assert np.array_equal(np.sign(w.cpu().numpy()), np.sign(a["w"]))
+
+    # LJ: sharded atoms against the one-GPU solve
+    a, c = res[0]["lj"], res[1]["lj"]
+    assert a["status"] == c["status"] and a["trace"] == c["trace"]
+    p0 = _lj_positions()
+    x = torch.tensor(p0, device="cuda:0")
+    tr = []
+    rep = R.lbfgs().with_max_iterations(25).minimize(x, R.LennardJones(),
+                                                   lambda p: tr.append((p.niter, p.neval, p.ncall, p.fx, p.gnorm)) and False)
+    assert rep.status_name == a["status"]
+    k = min(15, len(tr), len(a["trace"]))
+    assert [t[:3] for t in tr[:k]] == [t[:3] for t in a["trace"][:k]]
+    for s, t in zip(tr[:k], a["trace"][:k]):
+        assert abs(s[3] - t[3]) <= 1e-10 * abs(s[3]) and abs(s[4] - t[4]) <= 1e-8 * abs(s[4])
+    xs = np.concatenate([a["x"], c["x"]])
+    if len(tr) == len(a["trace"]):
+        assert np.max(np.abs(xs - x.cpu().numpy())) <= 1e-7 * np.max(np.abs(xs))
