@@ -120,7 +120,7 @@ struct OwlPgOp {
 template <bool S, bool HAS_D>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_owl_pg(OwlPgOp<S, HAS_D> op, int64_t n, ReduceWs ws, double *out) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    stream_pairs<4, HAS_D ? 2 : kU>(n, op, acc);   // three input vectors: U = 4 would not fit 64 registers
+    stream_pairs<4, HAS_D ? kUh : kU>(n, op, acc);   // 2R 1W (3R 1W with d): the tile shapes of the same traffic classes
     grid_reduce<4>(acc, ws, out);
 }
 
@@ -391,7 +391,7 @@ k_forward(ForwardOp<S, LAST, OWL> op, int64_t n, const double *red_in, double ys
     const double beta = __ldcg(red_in) / ys_j;              // lbfgs.rs:597
     op.coef = __ldcg(alpha_in) - beta;                      // :599
     double acc[3] = {0.0, 0.0, 0.0};
-    stream_pairs<3, (LAST && OWL) ? 2 : kU>(n, op, acc);
+    stream_pairs<3, kU>(n, op, acc);
     grid_reduce<3>(acc, ws, out);
 }
 
@@ -511,7 +511,7 @@ void launch_dots(const Launch &L, const double *g, const double *d, const double
 
 void launch_owl_pg(const Launch &L, double *pg, const double *x, const double *g, const double *d, int64_t n,
                    double c, int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, d ? 2 : kU);
+    const int grid = grid_for(L, n, d ? kUh : kU);
     count(L);
     if (d) {
         LB_DISPATCH_S(L,
@@ -616,7 +616,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
 void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
                     const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
                     int64_t start, int64_t end, int64_t goff, double *out) {
-    const int grid = grid_for(L, n, (last && owl) ? 2 : kU);
+    const int grid = grid_for(L, n, kU);
     count(L);
     const double *aux = last ? g_or_pg : y_next;
     if (L.streaming) forward_impl<true>(L, last, owl, r, s, aux, n, red_in, ys_j, alpha_in, start, end, goff, out, grid);

@@ -10,7 +10,14 @@ iters = int(os.environ.get("TUNE_ITERS", "30"))
 x = torch.empty(n, dtype=torch.float64, device="cuda:0")
 x[0::2] = -1.2
 x[1::2] = 1.0
-st = R.lbfgs().with_m(int(os.environ.get("TUNE_M", "6"))).build(x, R.Rosenbrock())
+b = R.lbfgs().with_m(int(os.environ.get("TUNE_M", "6")))
+if os.environ.get("TUNE_OWL"):
+    b = b.with_orthantwise(float(os.environ["TUNE_OWL"]), 0)
+if os.environ.get("TUNE_UNFUSED"):
+    b = b.with_fused_trial(False)
+if os.environ.get("TUNE_DAMPING"):
+    b = b.with_damping(True).with_linesearch_algorithm("BacktrackingStrongWolfe")
+st = b.build(x, R.Rosenbrock())
 for _ in range(8):
     st.propagate()
 st.profile_enable(os.environ.get("TUNE_TIMING", "1") != "0")
