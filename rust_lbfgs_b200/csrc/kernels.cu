@@ -292,8 +292,16 @@ struct DampOp {
     }
     __device__ __forceinline__ void tail(int64_t e, double (&)[1]) const { y[e] = elem(y[e], gp[e]); }
 };
+// The damping branch (src/lbfgs.rs:664-689) is taken on the device from the history kernel's sums, so the host
+// does not have to synchronise between the history update and the two-loop: hist = {s.s, y.s, y.y, s.(-g), s.Bs}.
 template <bool S>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) k_damp(DampOp<S> op, int64_t n) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_damp(DampOp<S> op, int64_t n, const double *hist) {
+    const double sigma2 = 0.6;                              // :664 (sigma3 = 3.0 selects case 2, which leaves y alone)
+    const double ys = __ldcg(hist + 1), sbs = __ldcg(hist + 4);
+    if (!(ys < (1.0 - sigma2) * sbs)) return;               // not case 1: y stays as it is (:681-689)
+    const double theta = sigma2 * sbs / (sbs - ys);         // :676
+    op.omt = 1.0 - theta;
+    op.theta = theta;
     double acc[1] = {0.0};
     stream_pairs<1, kU>(n, op, acc);
 }
@@ -336,11 +344,16 @@ struct BackwardOp {
 };
 template <bool S, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-k_backward(BackwardOp<S, FIRST, LAST> op, int64_t n, const double *red_in, double ys_j, double *alpha_out,
-           ReduceWs ws, double *out) {
+k_backward(BackwardOp<S, FIRST, LAST> op, int64_t n, const double *red_in, const double *ys_in, double *ys_store,
+           const double *hist, double *alpha_out, ReduceWs ws, double *out) {
+    const double ys_j = __ldcg(ys_in);                      // it.ys of slot j: a device scalar, never on the host path
     const double alpha = __ldcg(red_in) / ys_j;             // lbfgs.rs:587
-    if (blockIdx.x == 0 && threadIdx.x == 0) *alpha_out = alpha;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *alpha_out = alpha;
+        if (ys_store) *ys_store = ys_j;                     // the newest pair: keep y.s for the next m iterations (:653)
+    }
     op.nalpha = -alpha;
+    if (LAST) op.gamma = __ldcg(hist + 1) / __ldcg(hist + 2);  // gamma = ys / yy of the newest pair (:691)
     double acc[1] = {0.0};
     stream_pairs<1, kU>(n, op, acc);
     grid_reduce<1>(acc, ws, out);
@@ -386,9 +399,9 @@ struct ForwardOp {
 };
 template <bool S, bool LAST, bool OWL>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-k_forward(ForwardOp<S, LAST, OWL> op, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
+k_forward(ForwardOp<S, LAST, OWL> op, int64_t n, const double *red_in, const double *ys_in, const double *alpha_in,
           ReduceWs ws, double *out) {
-    const double beta = __ldcg(red_in) / ys_j;              // lbfgs.rs:597
+    const double beta = __ldcg(red_in) / __ldcg(ys_in);     // lbfgs.rs:597
     op.coef = __ldcg(alpha_in) - beta;                      // :599
     double acc[3] = {0.0, 0.0, 0.0};
     stream_pairs<3, kU>(n, op, acc);
@@ -572,19 +585,19 @@ void launch_history(const Launch &L, const double *x, const double *xp, const do
     else history_impl<false>(L, x, xp, g, gp, pg, s, y, n, nstep, damping, out, grid);
 }
 
-void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, double omt, double theta) {
+void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, const double *hist) {
     const int grid = grid_for(L, n, kU);
     count(L);
-    LB_DISPATCH_S(L, (k_damp<true><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)),
-                  (k_damp<false><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, omt, theta}, n)));
+    LB_DISPATCH_S(L, (k_damp<true><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, 0.0, 0.0}, n, hist)),
+                  (k_damp<false><<<grid, threads_for(L), 0, L.stream>>>({y, gp, nstep, 0.0, 0.0}, n, hist)));
 }
 
 template <bool S>
 static void backward_impl(const Launch &L, bool first, bool last, double *q, const double *g, const double *y,
-                          const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
-                          double *alpha_out, double *out, int grid) {
+                          const double *s_next, int64_t n, const double *red_in, const double *ys_in, double *ys_store,
+                          const double *hist, double *alpha_out, double *out, int grid) {
 #define LB_BWD(F, LA) \
-    k_backward<S, F, LA><<<grid, threads_for(L), 0, L.stream>>>({q, g, y, s_next, 0.0, gamma}, n, red_in, ys_j, alpha_out, ws_for(L), out)
+    k_backward<S, F, LA><<<grid, threads_for(L), 0, L.stream>>>({q, g, y, s_next, 0.0, 0.0}, n, red_in, ys_in, ys_store, hist, alpha_out, ws_for(L), out)
     if (first && last) LB_BWD(true, true);
     else if (first) LB_BWD(true, false);
     else if (last) LB_BWD(false, true);
@@ -593,17 +606,17 @@ static void backward_impl(const Launch &L, bool first, bool last, double *q, con
 }
 
 void launch_backward(const Launch &L, bool first, bool last, double *q, const double *g, const double *y,
-                     const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
-                     double *alpha_out, double *out) {
+                     const double *s_next, int64_t n, const double *red_in, const double *ys_in, double *ys_store,
+                     const double *hist, double *alpha_out, double *out) {
     const int grid = grid_for(L, n, kU);
     count(L);
-    if (L.streaming) backward_impl<true>(L, first, last, q, g, y, s_next, n, red_in, ys_j, gamma, alpha_out, out, grid);
-    else backward_impl<false>(L, first, last, q, g, y, s_next, n, red_in, ys_j, gamma, alpha_out, out, grid);
+    if (L.streaming) backward_impl<true>(L, first, last, q, g, y, s_next, n, red_in, ys_in, ys_store, hist, alpha_out, out, grid);
+    else backward_impl<false>(L, first, last, q, g, y, s_next, n, red_in, ys_in, ys_store, hist, alpha_out, out, grid);
 }
 
 template <bool S>
 static void forward_impl(const Launch &L, bool last, bool owl, double *r, const double *s, const double *aux,
-                         int64_t n, const double *red_in, double ys_j, const double *alpha_in, int64_t start,
+                         int64_t n, const double *red_in, const double *ys_j, const double *alpha_in, int64_t start,
                          int64_t end, int64_t goff, double *out, int grid) {
 #define LB_FWD(LA, OW) \
     k_forward<S, LA, OW><<<grid, threads_for(L), 0, L.stream>>>({r, s, aux, 0.0, start, end, goff}, n, red_in, ys_j, alpha_in, ws_for(L), out)
@@ -614,7 +627,7 @@ static void forward_impl(const Launch &L, bool last, bool owl, double *r, const 
 }
 
 void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
-                    const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
+                    const double *g_or_pg, int64_t n, const double *red_in, const double *ys_j, const double *alpha_in,
                     int64_t start, int64_t end, int64_t goff, double *out) {
     const int grid = grid_for(L, n, kU);
     count(L);

@@ -38,18 +38,21 @@ void launch_orthant(const Launch &L, signed char *wp, const double *xp, const do
 //     (pg != null: OWL-QN, the first alpha uses d = -pg)
 void launch_history(const Launch &L, const double *x, const double *xp, const double *g, const double *gp,
                     const double *pg, double *s, double *y, int64_t n, double nstep, bool damping, double *out);
-// K6  y = ((gp*nstep)*omt) + theta*y                         src/lbfgs.rs:675-680
-void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, double omt, double theta);
-// K7  alpha = *red_in / ys_j; q = (first ? -g : q) - alpha*y_j; !last: out = {s_next.q}
-//     last: d = q*gamma, out = {y_j.d}                        src/lbfgs.rs:582-591,597
+// K6  Powell damping, decided on the device from hist = K5's sums: if y.s < 0.4 s.Bs (case 1)
+//     y = ((gp*nstep)*(1-theta)) + theta*y with theta = 0.6 s.Bs / (s.Bs - y.s); otherwise the kernel exits at once
+//                                                            src/lbfgs.rs:664-689
+void launch_damp(const Launch &L, double *y, const double *gp, int64_t n, double nstep, const double *hist);
+// K7  alpha = *red_in / *ys_in; q = (first ? -g : q) - alpha*y_j; !last: out = {s_next.q}
+//     last: d = q*gamma with gamma = hist[1] / hist[2] (y.s / y.y of the newest pair), out = {y_j.d}
+//     ys_in, hist, red_in are DEVICE scalars (ys_store != null: *ys_store = *ys_in)   src/lbfgs.rs:582-591,597,691
 void launch_backward(const Launch &L, bool first, bool last, double *q, const double *g, const double *y,
-                     const double *s_next, int64_t n, const double *red_in, double ys_j, double gamma,
-                     double *alpha_out, double *out);
-// K8  beta = *red_in / ys_j; r += (alpha_j - beta) s_j; !last: out = {y_next.r}
+                     const double *s_next, int64_t n, const double *red_in, const double *ys_in, double *ys_store,
+                     const double *hist, double *alpha_out, double *out);
+// K8  beta = *red_in / *ys_j (device scalar); r += (alpha_j - beta) s_j; !last: out = {y_next.r}
 //     last: out = {r.r, g.r}; last+owl: out = {r.r (before projection), pg.d, d.d (after)}
 //                                                            src/lbfgs.rs:594-601,543, src/orthantwise.rs:140-161
 void launch_forward(const Launch &L, bool last, bool owl, double *r, const double *s, const double *y_next,
-                    const double *g_or_pg, int64_t n, const double *red_in, double ys_j, const double *alpha_in,
+                    const double *g_or_pg, int64_t n, const double *red_in, const double *ys_j, const double *alpha_in,
                     int64_t start, int64_t end, int64_t goff, double *out);
 // OWL-QN direction projection alone (K8's epilogue as a stand-alone op): out = {d.d after}
 void launch_owl_constrain(const Launch &L, double *d, const double *pg, int64_t n, int64_t start, int64_t end,

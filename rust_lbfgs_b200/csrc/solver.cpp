@@ -258,9 +258,8 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     Y_.resize(m_);
     for (int64_t i = 0; i < m_; ++i) { S_[i] = take(); Y_[i] = take(); }
     if (owl_) wp_ = (signed char *)base;
-    ys_.assign(m_, 0.0);
 
-    const size_t scal_need = SLOT_COUNT * kMaxAcc + (size_t)m_;
+    const size_t scal_need = SLOT_COUNT * kMaxAcc + 2 * (size_t)m_;   // slots, alpha[m], ys[m]
     Scratch sc;
     rc = scratch_acquire(dev_, scal_need, &sc);
     if (rc != 0) return fail(rc, "cudaMalloc(scalars / pinned mirror / reduce workspace)");
@@ -273,6 +272,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     e = cudaMemsetAsync(ws_.ticket, 0, 256, stream_);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ticket)");
     alpha_dev_ = scal_dev_ + SLOT_COUNT * kMaxAcc;
+    ys_dev_ = alpha_dev_ + m_;
     tm.lap("create: scalars + pinned + workspace");
 
     // evict-first accesses once the working set cannot live in L2
@@ -359,6 +359,20 @@ int Solver::fetch(int s, int count, double *host, bool ours) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
     if (timing_) prof_resolve();
     for (int i = 0; i < count; ++i) host[i] = scal_host_[i];
+    return 0;
+}
+
+// Two slots (already summed over the ranks) with one synchronisation.
+int Solver::fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2) {
+    cudaError_t e = cudaMemcpyAsync(scal_host_, slot(s1), sizeof(double) * c1, cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scal_host_ + kMaxAcc, slot(s2), sizeof(double) * c2, cudaMemcpyDeviceToHost, stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H scalars)");
+    e = cudaStreamSynchronize(stream_);
+    prof_.host_syncs += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if (timing_) prof_resolve();
+    for (int i = 0; i < c1; ++i) h1[i] = scal_host_[i];
+    for (int i = 0; i < c2; ++i) h2[i] = scal_host_[kMaxAcc + i];
     return 0;
 }
 
@@ -576,41 +590,28 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     }
     ncall_ = ls.ncall();
 
-    // IterationData::update, src/lbfgs.rs:640-692
+    // IterationData::update, src/lbfgs.rs:640-692.  Everything from here to the end of the two-loop is enqueued
+    // without a host round trip: y.s, y.y, gamma and the damping branch are consumed on the device, and the host
+    // checks the history sums (`x not changed` / `gx not changed`) when it reads the final dot products.
     const int64_t slot_new = end_;
     const bool damping = p_.damping != 0;
+    double *hist = slot(SLOT_HIST);   // {s.s, y.s, y.y, s.(-g | -pg), s.Bs}
     prof_begin(LBFGSB200_K_HISTORY);
-    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, slot(SLOT_HIST));
+    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, hist);
     prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
-    double h[5];
-    int rc = fetch(SLOT_HIST, 5, h);
-    if (rc != 0) return rc;
-    const double ss = h[0], ys = h[1], yy = h[2], sbs = h[4];
-    if (!(std::sqrt(ss) != 0.0)) {  // :645-646
-        char msg[96];
-        snprintf(msg, sizeof(msg), "x not changed with step %g", step_);
-        return fail(LBFGSB200_ERR_X_NOT_CHANGED, msg);
+    int rc = reduce_across_ranks(SLOT_HIST, 5);
+    if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    if (damping) {  // :664-689, decided inside the kernel (case 1 rewrites y, otherwise it exits at once)
+        prof_begin(LBFGSB200_K_DAMP);
+        launch_damp(L, Y_[slot_new], gp, n_, -step_, hist);
+        prof_end(LBFGSB200_K_DAMP, 0.0);
     }
-    if (!(yy != 0.0)) return fail(LBFGSB200_ERR_G_NOT_CHANGED, "gx not changed");  // :655
-    ys_[slot_new] = ys;
-    if (damping) {  // :664-689
-        const double sigma2 = 0.6, sigma3 = 3.0;
-        if (ys < (1.0 - sigma2) * sbs) {  // case 1: y is replaced
-            const double theta = sigma2 * sbs / (sbs - ys);
-            prof_begin(LBFGSB200_K_DAMP);
-            launch_damp(L, Y_[slot_new], gp, n_, -step_, 1.0 - theta, theta);
-            prof_end(LBFGSB200_K_DAMP, 3.0 * vbytes);
-        } else if (ys > (1.0 + sigma3) * sbs) {
-            // case 2 computes a damped vector and drops it (:681-685): y stays as it is
-        }
-    }
-    const double gamma = ys / yy;  // :691
 
     // lbfgs_two_loop_recursion, src/lbfgs.rs:569-604, one fused kernel per trip
     end_ = (end_ + 1) % m_;
     const int64_t bound = (m_ < k_ - 1) ? m_ : (k_ - 1);
     int64_t j = end_;
-    const double *red_in = slot(SLOT_HIST) + 3;  // s_new . (-g), produced by the history kernel
+    const double *red_in = hist + 3;              // s_new . (-g), produced by the history kernel
     int pp = 0;
     const double *dsrc = owl_ ? pg_ : g;          // d = -g | -pg, core.rs:95-101
     for (int64_t t = 0; t < bound; ++t) {
@@ -618,8 +619,11 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         const bool first = (t == 0), last = (t == bound - 1);
         const int64_t jn = (j + m_ - 1) % m_;
         const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
+        // it.ys of the newest pair still sits in the history slot; the first trip files it into ys_dev[slot_new]
+        const double *ys_in = first ? hist + 1 : ys_dev_ + j;
         prof_begin(LBFGSB200_K_BACKWARD);
-        launch_backward(L, first, last, d_, dsrc, Y_[j], last ? nullptr : S_[jn], n_, red_in, ys_[j], gamma, alpha_dev_ + j, slot(so));
+        launch_backward(L, first, last, d_, dsrc, Y_[j], last ? nullptr : S_[jn], n_, red_in, ys_in,
+                        first ? ys_dev_ + j : nullptr, hist, alpha_dev_ + j, slot(so));
         prof_end(LBFGSB200_K_BACKWARD, (last ? 3.0 : 4.0) * vbytes);
         rc = reduce_across_ranks(so, 1);
         if (rc != 0) return fail(rc, "ncclAllReduce failed");
@@ -632,21 +636,28 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         const int64_t jn = (j + 1) % m_;
         const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
         prof_begin(LBFGSB200_K_FORWARD);
-        launch_forward(L, last, owl_, d_, S_[j], last ? nullptr : Y_[jn], dsrc, n_, red_in, ys_[j], alpha_dev_ + j,
+        launch_forward(L, last, owl_, d_, S_[j], last ? nullptr : Y_[jn], dsrc, n_, red_in, ys_dev_ + j, alpha_dev_ + j,
                        owl_start_, owl_end_, goff_, slot(so));
         prof_end(LBFGSB200_K_FORWARD, 4.0 * vbytes);
-        if (!last) {
-            rc = reduce_across_ranks(so, 1);
-            if (rc != 0) return fail(rc, "ncclAllReduce failed");
-        }
+        rc = reduce_across_ranks(so, last ? 3 : 1);
+        if (rc != 0) return fail(rc, "ncclAllReduce failed");
         red_in = slot(so);
         so_last = so;
         pp ^= 1;
         j = jn;
     }
-    double hd[3];
-    rc = fetch(so_last, 3, hd);
+    // the one host round trip of the update: the history sums and the final dot products together
+    double h[5], hd[3];
+    rc = fetch2(SLOT_HIST, 5, h, so_last, 3, hd);
     if (rc != 0) return rc;
+    const double ss = h[0], ys = h[1], yy = h[2], sbs = h[4];
+    if (!(std::sqrt(ss) != 0.0)) {  // :645-646
+        char msg[96];
+        snprintf(msg, sizeof(msg), "x not changed with step %g", step_);
+        return fail(LBFGSB200_ERR_X_NOT_CHANGED, msg);
+    }
+    if (!(yy != 0.0)) return fail(LBFGSB200_ERR_G_NOT_CHANGED, "gx not changed");  // :655
+    if (damping && ys < (1.0 - 0.6) * sbs) prof_.bytes[LBFGSB200_K_DAMP] += 3.0 * vbytes;  // case 1 ran (accounting only)
     const double dnorm = std::sqrt(hd[0]);  // :543 (before the orthant projection)
     dginit_ = hd[1];
     if (std::signbit(dnorm)) return fail(LBFGSB200_ERR_INVALID_DNORM, "invalid norm value");  // :544

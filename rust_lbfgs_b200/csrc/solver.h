@@ -4,8 +4,9 @@
 // every n-vector lives in HBM: it owns g/gp (ping-pong), the second x buffer, d, pg, wp and the
 // 2m-vector s/y ring, launches the fused kernels of kernels.cu on one stream, and keeps only
 // scalars on the host.  The host synchronises where the scalar logic needs a value: once per
-// line-search trial (f, dg), once after the history update (ys, yy for the error checks / damping)
-// and once after the two-loop (||d|| for the next step).
+// line-search trial (f, dg) and once per iteration after the two-loop (||d|| for the next step, together
+// with the history sums for the `x not changed` / `gx not changed` checks); y.s, gamma and the Powell
+// damping branch are consumed on the device.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -84,6 +85,7 @@ class Solver {
     bool finish_eval(bool fused, double *dg_out);                  // allreduce + D2H + sync of SLOT_EVAL
     void post_eval_flag(int erc);
     int fetch(int s, int count, double *host, bool ours = true);   // allreduce + D2H + sync of a slot
+    int fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2);  // two reduced slots, one sync
     // ours = the slot was produced by one of our reducing kernels (already exchanged inside it with peer mailboxes)
     int reduce_across_ranks(int s, int count, bool ours = true);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
@@ -117,6 +119,7 @@ class Solver {
     std::vector<double *> S_, Y_;
     double *scal_dev_ = nullptr;    // SLOT_COUNT * kMaxAcc doubles, then alpha[m]
     double *alpha_dev_ = nullptr;
+    double *ys_dev_ = nullptr;      // y.s of every ring slot (src/lbfgs.rs:613 `ys`), device-only
     double *scal_host_ = nullptr;   // pinned mirror of one slot
     size_t scal_count_ = 0;         // doubles behind scal_dev_ (the buffers are recycled, see solver.cpp)
     ReduceWs ws_{};
@@ -134,7 +137,6 @@ class Solver {
     int64_t k_ = 0, end_ = 0, ncall_ = 0, neval_ = 0;
     int64_t last_ls_error_ = 0;
     int last_status_ = 0;
-    std::vector<double> ys_;
     std::string err_;
 
     // profile
