@@ -156,6 +156,7 @@ int trim_pool(int device) {
 
 Solver::~Solver() {
     DbgTimer tm;
+    drop_graphs();
     for (auto &p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
     for (auto e : event_pool_) cudaEventDestroy(e);
     tm.lap("destroy: events");
@@ -282,6 +283,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     if (force == 0) streaming_ = false;
     if (force == 1) streaming_ = true;
     memset(&prof_, 0, sizeof(prof_));
+    graphs_enabled_ = env_int("LBFGSB200_GRAPHS", 1) != 0;
     return 0;
 }
 
@@ -487,6 +489,7 @@ int Solver::build(double *x_dev, lbfgsb200_eval_fn eval, void *user) {
     if (((uintptr_t)x_dev & 15u) != 0) return fail(LBFGSB200_ERR_INVALID_PARAM, "x_dev must be 16-byte aligned");
     cudaError_t e = cudaSetDevice(dev_.device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (xbuf_[0] != x_dev) drop_graphs();   // captured chains hold the caller's x pointer
     xbuf_[0] = x_dev;
     cur_x_ = 0;
     cur_g_ = 0;
@@ -530,6 +533,135 @@ bool Solver::is_converged(int *stop_status) {
     return true;
 }
 
+// ---- the update chain of one iteration: history (+ damping) + two-loop ------------------------------------------
+int Solver::enqueue_update(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last) {
+    // Everything here is enqueued without a host round trip: y.s, y.y, gamma and the damping branch are consumed
+    // on the device, and the host checks the history sums (`x not changed` / `gx not changed`) when it reads the
+    // final dot products.
+    const int64_t slot_new = end_;
+    const bool damping = p_.damping != 0;
+    const double vbytes = 8.0 * (double)n_;
+    const double *x = xbuf_[cur_x_];
+    const double *g = gbuf_[cur_g_];
+    double *hist = slot(SLOT_HIST);   // {s.s, y.s, y.y, s.(-g | -pg), s.Bs}
+    prof_begin(LBFGSB200_K_HISTORY);
+    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, hist);
+    prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
+    int rc = reduce_across_ranks(SLOT_HIST, 5);
+    if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    if (damping) {  // :664-689, decided inside the kernel (case 1 rewrites y, otherwise it exits at once)
+        prof_begin(LBFGSB200_K_DAMP);
+        launch_damp(L, Y_[slot_new], gp, n_, -step_, hist);
+        prof_end(LBFGSB200_K_DAMP, 0.0);
+    }
+
+    // lbfgs_two_loop_recursion, src/lbfgs.rs:569-604, one fused kernel per trip (end = (end + 1) % m, :575)
+    int64_t j = (end_ + 1) % m_;
+    const double *red_in = hist + 3;              // s_new . (-g), produced by the history kernel
+    int pp = 0;
+    const double *dsrc = owl_ ? pg_ : g;          // d = -g | -pg, core.rs:95-101
+    for (int64_t t = 0; t < bound; ++t) {
+        j = (j + m_ - 1) % m_;
+        const bool first = (t == 0), last = (t == bound - 1);
+        const int64_t jn = (j + m_ - 1) % m_;
+        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
+        // it.ys of the newest pair still sits in the history slot; the first trip files it into ys_dev[slot_new]
+        const double *ys_in = first ? hist + 1 : ys_dev_ + j;
+        prof_begin(LBFGSB200_K_BACKWARD);
+        launch_backward(L, first, last, d_, dsrc, Y_[j], last ? nullptr : S_[jn], n_, red_in, ys_in,
+                        first ? ys_dev_ + j : nullptr, hist, alpha_dev_ + j, slot(so));
+        prof_end(LBFGSB200_K_BACKWARD, (last ? 3.0 : 4.0) * vbytes);
+        rc = reduce_across_ranks(so, 1);
+        if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        red_in = slot(so);
+        pp ^= 1;
+    }
+    for (int64_t t = 0; t < bound; ++t) {
+        const bool last = (t == bound - 1);
+        const int64_t jn = (j + 1) % m_;
+        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
+        prof_begin(LBFGSB200_K_FORWARD);
+        launch_forward(L, last, owl_, d_, S_[j], last ? nullptr : Y_[jn], dsrc, n_, red_in, ys_dev_ + j, alpha_dev_ + j,
+                       owl_start_, owl_end_, goff_, slot(so));
+        prof_end(LBFGSB200_K_FORWARD, 4.0 * vbytes);
+        rc = reduce_across_ranks(so, last ? 3 : 1);
+        if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        red_in = slot(so);
+        *so_last = so;
+        pp ^= 1;
+        j = jn;
+    }
+    return 0;
+}
+
+// CUDA-graph replay of enqueue_update for the launch-bound regime.  The kernel arguments of the chain depend only
+// on the ring position (which s/y slots), the x/g buffer parity and — fixed for a solver — the option set, so
+// after the history ring is full there are at most 2m distinct chains; each is captured once and then replayed
+// with a single cudaGraphLaunch (1 + 2m kernels cost ~4.5 us of CPU launch time each otherwise).
+bool Solver::graph_eligible(int64_t bound) const {
+    if (!graphs_enabled_ || timing_ || sequential_ || p_.damping != 0) return false;   // damping passes -step by value
+    if (comm_ && comm_size(comm_) > 1) return false;                                   // exchange sequence numbers are by value
+    if (bound != m_) return false;                                                     // ring still filling
+    // capturing + instantiating one chain costs about as much as 6 iterations of direct launches and saves
+    // ~20 us per replay (measured, profiles/README.md): only long solves get graphs
+    if (k_ <= 10 * m_ + 4) return false;
+    return n_ <= kGraphMaxN;
+}
+
+int Solver::update_graphed(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last) {
+    if (!cap_stream_) {
+        if (cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            graphs_enabled_ = false;
+            return enqueue_update(L, xp, gp, bound, so_last);
+        }
+        graphs_.assign((size_t)(2 * m_), GraphEntry{});
+    }
+    GraphEntry &ge = graphs_[(size_t)(end_ * 2 + cur_x_)];
+    if (!ge.exec) {
+        const lbfgsb200_profile_t before = prof_;
+        const int64_t launches_before = launch_counter_;
+        Launch Lc = L;
+        Lc.stream = cap_stream_;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int rc = ok ? enqueue_update(Lc, xp, gp, bound, &ge.so_last) : 0;
+        if (ok) ok = cudaStreamEndCapture(cap_stream_, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+        if (ok) ok = cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        // nothing ran during the capture: take the counters back, they are added per replay below
+        for (int k = 0; k < LBFGSB200_K_COUNT; ++k) {
+            ge.launches[k] = prof_.launches[k] - before.launches[k];
+            ge.bytes[k] = prof_.bytes[k] - before.bytes[k];
+        }
+        ge.kernels = launch_counter_ - launches_before;
+        prof_ = before;
+        launch_counter_ = launches_before;
+        if (!ok) {
+            cudaGetLastError();
+            ge.exec = nullptr;
+            graphs_enabled_ = false;
+            return enqueue_update(L, xp, gp, bound, so_last);
+        }
+    }
+    if (cudaGraphLaunch(ge.exec, stream_) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGraphLaunch");
+    for (int k = 0; k < LBFGSB200_K_COUNT; ++k) {
+        prof_.launches[k] += ge.launches[k];
+        prof_.bytes[k] += ge.bytes[k];
+    }
+    launch_counter_ += ge.kernels;
+    graph_replays_ += 1;
+    *so_last = ge.so_last;
+    return 0;
+}
+
+void Solver::drop_graphs() {
+    for (auto &ge : graphs_)
+        if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    graphs_.clear();
+    if (cap_stream_) { cudaStreamDestroy(cap_stream_); cap_stream_ = nullptr; }
+}
+
 // ---- LbfgsState::propagate, src/lbfgs.rs:503-560 ----------------------------------------------
 int Solver::propagate(lbfgsb200_progress_t *out) {
     if (!built_) return fail(LBFGSB200_ERR_STATE, "propagate() before build()");
@@ -549,8 +681,6 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     const double xx_prev = xx_, gg_prev = gg_;
     cur_x_ ^= 1;
     cur_g_ ^= 1;
-    double *x = xbuf_[cur_x_];
-    double *g = gbuf_[cur_g_];
     auto revert = [&]() {  // core.rs:201-204: x, gx restored; fx and pg are not
         cur_x_ ^= 1;
         cur_g_ ^= 1;
@@ -590,62 +720,17 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     }
     ncall_ = ls.ncall();
 
-    // IterationData::update, src/lbfgs.rs:640-692.  Everything from here to the end of the two-loop is enqueued
-    // without a host round trip: y.s, y.y, gamma and the damping branch are consumed on the device, and the host
-    // checks the history sums (`x not changed` / `gx not changed`) when it reads the final dot products.
-    const int64_t slot_new = end_;
+    // IterationData::update (src/lbfgs.rs:640-692) + lbfgs_two_loop_recursion (:569-604): 1 + 2*bound kernels with no
+    // host round trip in between.  In the launch-bound regime (small n, steady state) the chain is captured once
+    // per (ring position, buffer parity) into a CUDA graph and replayed with one launch.
     const bool damping = p_.damping != 0;
-    double *hist = slot(SLOT_HIST);   // {s.s, y.s, y.y, s.(-g | -pg), s.Bs}
-    prof_begin(LBFGSB200_K_HISTORY);
-    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, hist);
-    prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
-    int rc = reduce_across_ranks(SLOT_HIST, 5);
-    if (rc != 0) return fail(rc, "ncclAllReduce failed");
-    if (damping) {  // :664-689, decided inside the kernel (case 1 rewrites y, otherwise it exits at once)
-        prof_begin(LBFGSB200_K_DAMP);
-        launch_damp(L, Y_[slot_new], gp, n_, -step_, hist);
-        prof_end(LBFGSB200_K_DAMP, 0.0);
-    }
-
-    // lbfgs_two_loop_recursion, src/lbfgs.rs:569-604, one fused kernel per trip
-    end_ = (end_ + 1) % m_;
     const int64_t bound = (m_ < k_ - 1) ? m_ : (k_ - 1);
-    int64_t j = end_;
-    const double *red_in = hist + 3;              // s_new . (-g), produced by the history kernel
-    int pp = 0;
-    const double *dsrc = owl_ ? pg_ : g;          // d = -g | -pg, core.rs:95-101
-    for (int64_t t = 0; t < bound; ++t) {
-        j = (j + m_ - 1) % m_;
-        const bool first = (t == 0), last = (t == bound - 1);
-        const int64_t jn = (j + m_ - 1) % m_;
-        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
-        // it.ys of the newest pair still sits in the history slot; the first trip files it into ys_dev[slot_new]
-        const double *ys_in = first ? hist + 1 : ys_dev_ + j;
-        prof_begin(LBFGSB200_K_BACKWARD);
-        launch_backward(L, first, last, d_, dsrc, Y_[j], last ? nullptr : S_[jn], n_, red_in, ys_in,
-                        first ? ys_dev_ + j : nullptr, hist, alpha_dev_ + j, slot(so));
-        prof_end(LBFGSB200_K_BACKWARD, (last ? 3.0 : 4.0) * vbytes);
-        rc = reduce_across_ranks(so, 1);
-        if (rc != 0) return fail(rc, "ncclAllReduce failed");
-        red_in = slot(so);
-        pp ^= 1;
-    }
     int so_last = SLOT_LOOP_A;
-    for (int64_t t = 0; t < bound; ++t) {
-        const bool last = (t == bound - 1);
-        const int64_t jn = (j + 1) % m_;
-        const int so = pp ? SLOT_LOOP_B : SLOT_LOOP_A;
-        prof_begin(LBFGSB200_K_FORWARD);
-        launch_forward(L, last, owl_, d_, S_[j], last ? nullptr : Y_[jn], dsrc, n_, red_in, ys_dev_ + j, alpha_dev_ + j,
-                       owl_start_, owl_end_, goff_, slot(so));
-        prof_end(LBFGSB200_K_FORWARD, 4.0 * vbytes);
-        rc = reduce_across_ranks(so, last ? 3 : 1);
-        if (rc != 0) return fail(rc, "ncclAllReduce failed");
-        red_in = slot(so);
-        so_last = so;
-        pp ^= 1;
-        j = jn;
-    }
+    int rc = 0;
+    if (graph_eligible(bound)) rc = update_graphed(L, xp, gp, bound, &so_last);
+    else rc = enqueue_update(L, xp, gp, bound, &so_last);
+    if (rc != 0) return rc;
+    end_ = (end_ + 1) % m_;
     // the one host round trip of the update: the history sums and the final dot products together
     double h[5], hd[3];
     rc = fetch2(SLOT_HIST, 5, h, so_last, 3, hd);

@@ -90,6 +90,11 @@ class Solver {
     int reduce_across_ranks(int s, int count, bool ours = true);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
     Launch launch_cfg();
+    // history (+ damping) + two-loop of one iteration, enqueued on L.stream; *so_last = slot of the final dots
+    int enqueue_update(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last);
+    bool graph_eligible(int64_t bound) const;
+    int update_graphed(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last);
+    void drop_graphs();
 
     // timing instrumentation
     struct Pending { int kind; cudaEvent_t a, b; };
@@ -138,6 +143,20 @@ class Solver {
     int64_t last_ls_error_ = 0;
     int last_status_ = 0;
     std::string err_;
+
+    // CUDA graphs of the update chain (launch-bound regime: n <= kGraphMaxN), one per (ring position, parity)
+    static constexpr int64_t kGraphMaxN = 1 << 22;
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int so_last = 0;
+        int64_t kernels = 0;
+        int64_t launches[LBFGSB200_K_COUNT] = {};
+        double bytes[LBFGSB200_K_COUNT] = {};
+    };
+    std::vector<GraphEntry> graphs_;
+    cudaStream_t cap_stream_ = nullptr;
+    bool graphs_enabled_ = true;     // LBFGSB200_GRAPHS=0 disables
+    int64_t graph_replays_ = 0;
 
     // profile
     bool timing_ = false;
