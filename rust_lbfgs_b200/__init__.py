@@ -3,7 +3,7 @@ builder API.  All compute is hand-written CUDA in liblbfgsb200.so (include/lbfgs
 package is the thin host mirror of `liblbfgs` (ybyygu/rust-lbfgs): `lbfgs()`, `Lbfgs.with_*`,
 `minimize`, `build`/`propagate`, `Progress`, `Report`.  No CPU fallback, no other backend."""
 from ._lib import build_library, lib, default_param, STATUS_NAMES  # noqa: F401
-from .api import Lbfgs, LbfgsError, LbfgsState, Progress, Report, lbfgs, device_view  # noqa: F401
+from .api import Lbfgs, LbfgsError, LbfgsState, Progress, Report, lbfgs, device_view, host_evaluate  # noqa: F401
 from .objectives import Booth, Glm, LennardJones, Rosenbrock  # noqa: F401
 from . import dist  # noqa: F401
 

@@ -135,6 +135,24 @@ class _Evaluate:
             raise TypeError("evaluate must be a built-in objective or a callable evaluate(x, gx) -> fx")
 
 
+def host_evaluate(fn):
+    """Adapter for a reference-style HOST closure `fn(x: np.ndarray, gx: np.ndarray) -> fx | None` (the shape of
+    `E: FnMut(&[f64], &mut [f64]) -> Result<f64>`, src/core.rs:10-13; None = Err).  x is copied to the host, gx
+    and fx back: one PCIe round trip per evaluation — for porting existing objectives, not for speed.  The solver's
+    own vector algebra stays on the GPU."""
+    import numpy as np
+
+    def evaluate(x, gx):
+        xh = x.detach().cpu().numpy()
+        gh = np.zeros_like(xh)
+        fx = fn(xh, gh)
+        if fx is None:
+            return None
+        gx.copy_(gx.new_tensor(gh))
+        return float(fx)
+    return evaluate
+
+
 class _null:
     def __enter__(self):
         return self

@@ -78,6 +78,20 @@ def test_p4_booth_python_callable_evaluate(oracle):
     assert abs(got["x"][0] - 1.0) <= 1e-6 and abs(got["x"][1] - 3.0) <= 1e-6
 
 
+def test_p4_booth_host_closure_like_the_reference(oracle):
+    """tests/simple.rs:57-83 verbatim: a HOST closure on slices, through the host_evaluate adapter."""
+    def booth(x, gx):
+        x1, x2 = x[0], x[1]
+        gx[0] = 10.0 * x1 + 8.0 * x2 - 34.0
+        gx[1] = 8.0 * x1 + 10.0 * x2 - 38.0
+        return (x1 + 2.0 * x2 - 7.0) ** 2 + (2.0 * x1 + x2 - 5.0) ** 2
+    ref = oracle_run(oracle, [-1.2, 1.0], oracle.Objective.builtin("booth"))
+    got = gpu_minimize(R.lbfgs(), [-1.2, 1.0], R.host_evaluate(booth))
+    assert got["status_name"] == ref["status_name"] == "OK_CONVERGED"
+    assert len(got["trace"]) == len(ref["trace"]) and got["report"].neval == ref["report"]["neval"]
+    assert abs(got["x"][0] - 1.0) <= 1e-6 and abs(got["x"][1] - 3.0) <= 1e-6
+
+
 # ---- P5: tests/owlqn.rs:5-63 ------------------------------------------------------------------------------
 def test_p5_owlqn_poisson_fixture(oracle, golden_dir):
     from gpu_util import dev
