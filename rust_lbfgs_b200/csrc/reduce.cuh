@@ -144,19 +144,48 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NACC], const ReduceWs 
     }
 }
 
-// 128-bit streaming loads/stores.  kStream selects evict-first (.cs) accesses for vectors that are
-// far larger than L2 (n = 1e8: 0.8 GB per vector vs 126 MB of L2); small problems keep default
-// caching so the working set stays L2-resident between kernels.
+// 128-bit streaming loads/stores.  kStream marks the instantiations used when the vectors are far larger than L2
+// (n = 1e8: 0.8 GB per vector vs 126 MB of L2); which cache hints they use is a build-time policy (below).
+// Cache hints for the streaming (working set >> L2) instantiations, measured on B200 at n = 1e8
+// (profiles/r01_tuning.md): evict-first loads (ld.global.cs) cost 4 % on most boxes (6.70 vs 7.00 TB/s for the
+// 3R 1W kernels), no-allocate loads are no better, and evict-first / .cg stores only help together with plain
+// loads.  Plain loads and stores are the robust choice, so the hints are off by default.
+#ifndef LB_LD_POLICY
+#define LB_LD_POLICY 1   // 0 = ld.global.cs (evict-first), 1 = default, 2 = ld.global.nc.L1::no_allocate
+#endif
+#ifndef LB_ST_POLICY
+#define LB_ST_POLICY 1   // 0 = st.global.cs (evict-first), 1 = default, 2 = st.global.cg
+#endif
 template <bool kStream>
 __device__ __forceinline__ double2 ld2(const double *__restrict__ p, int64_t i) {
     const double2 *q = reinterpret_cast<const double2 *>(p) + i;
-    if (kStream) return __ldcs(q);
+    if (kStream) {
+#if LB_LD_POLICY == 0
+        return __ldcs(q);
+#elif LB_LD_POLICY == 2
+        double2 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q));
+        return v;
+#else
+        return *q;
+#endif
+    }
     return *q;
 }
 template <bool kStream>
 __device__ __forceinline__ void st2(double *__restrict__ p, int64_t i, double2 v) {
     double2 *q = reinterpret_cast<double2 *>(p) + i;
-    if (kStream) __stcs(q, v); else *q = v;
+    if (kStream) {
+#if LB_ST_POLICY == 0
+        __stcs(q, v);
+#elif LB_ST_POLICY == 2
+        __stcg(q, v);
+#else
+        *q = v;
+#endif
+    } else {
+        *q = v;
+    }
 }
 
 // Streams n elements through `op` as double2 pairs: U independent 128-bit loads per input vector

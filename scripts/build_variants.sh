@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/../rust_lbfgs_b200/csrc"
 build() {  # name U MINBLOCKS UH [THREADS]
   mkdir -p ../../build/variants
-  make -s -j8 OUT=../../build/variants/lib_$1.so OBJDIR=../../build/obj_$1 EXTRA="-DLB_U=$2 -DLB_MINBLOCKS=$3 -DLB_UH=$4 -DLB_THREADS=${5:-256} -DLB_UT=${6:-$2}" 2>&1 | grep -i "error" || true
+  make -s -j8 OUT=../../build/variants/lib_$1.so OBJDIR=../../build/obj_$1 EXTRA="-DLB_U=$2 -DLB_MINBLOCKS=$3 -DLB_UH=$4 -DLB_THREADS=${5:-256} -DLB_UT=${6:-$2} ${EXTRA2:-}" 2>&1 | grep -i "error" || true
 }
 for v in "$@"; do
   case $v in
@@ -19,6 +19,11 @@ for v in "$@"; do
     t512u2b2) build t512u2b2 2 2 1 512;;
     t128u8b4) build t128u8b4 8 4 4 128;;
     t128u16b2) build t128u16b2 16 2 8 128;;
+    ld1st0) EXTRA2="-DLB_LD_POLICY=1 -DLB_ST_POLICY=0" build ld1st0 8 2 4 256 6;;
+    ld0st1) EXTRA2="-DLB_LD_POLICY=0 -DLB_ST_POLICY=1" build ld0st1 8 2 4 256 6;;
+    ld1st1) EXTRA2="-DLB_LD_POLICY=1 -DLB_ST_POLICY=1" build ld1st1 8 2 4 256 6;;
+    ld0st2) EXTRA2="-DLB_LD_POLICY=0 -DLB_ST_POLICY=2" build ld0st2 8 2 4 256 6;;
+    ld2st0) EXTRA2="-DLB_LD_POLICY=2 -DLB_ST_POLICY=0" build ld2st0 8 2 4 256 6;;
     vA) build vA 6 1 3 256 5;;
     vB) build vB 7 1 4 256 6;;
     vC) build vC 8 1 5 256 7;;
