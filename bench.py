@@ -301,24 +301,18 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API with HOST buffers: `e2e` ---------------------------------
-    # The reference-shaped call: x is a host slice (src/lbfgs.rs:399).  Timed: pinned host -> device copy
-    # of x0, a complete minimize() of W+K iterations (build + line searches + two-loops), device -> host
-    # copy of the result.  Copies happen once per solve, so bytes/step are 8n/(W+K) each way (+ the few
-    # scalars the solver reads back per iteration).
+    # The reference-shaped call: x is a HOST slice (src/lbfgs.rs:399), passed to the C ABI's host-buffer entry.
+    # Timed: the whole call — pinned host -> device copy of x0, solver creation, a complete minimize() of W+K
+    # iterations (build + line searches + two-loops), device -> host copy of the result, teardown.  The copies
+    # happen once per solve, so bytes/step are 8n/(W+K) each way (+ the few scalars read back per iteration).
     iters_e2e = W + K
     xh = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
     fill_x0(xh)
-    xd = torch.empty(n_local, dtype=torch.float64, device=dev)
     builder = make_builder().with_max_iterations(iters_e2e + 1)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    xd.copy_(xh, non_blocking=True)
-    ta = time.perf_counter()
-    rep = builder.minimize(xd, obj, None)
-    tb = time.perf_counter()
-    xh.copy_(xd, non_blocking=True)
-    torch.cuda.synchronize()
+    rep = builder.minimize_host(xh, obj, None, device=local_rank)   # ONE C-ABI call: lbfgsb200_minimize_host_ex
     t1 = time.perf_counter()
     barrier()
     e2e_s = D.max_over_ranks(t1 - t0)
@@ -328,10 +322,10 @@ def run_ours(args):
         "h2d_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters),
         "d2h_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters) + 64.0 * 3,
         "iterations": e2e_iters, "seconds": e2e_s, "evaluations": rep.neval,
-        "host_seconds": {"enqueue_h2d": ta - t0, "minimize_call": tb - ta, "d2h_and_sync": t1 - tb},
-        "note": "host x0 (pinned) -> HBM, full minimize() of W+K iterations incl. build, HBM -> host x",
+        "note": "one lbfgsb200_minimize_host_ex() call on a pinned HOST buffer: H2D of x0, solver creation, build, "
+                "W+K iterations, D2H of x, teardown",
     }
-    del xd, xh
+    del xh
 
     # ---- the reference's CPU path on this host (rank 0, N=1 only) -------------------------------------
     cpu = None

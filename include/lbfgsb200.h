@@ -222,6 +222,13 @@ int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int6
                             lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
                             void *progress_user, lbfgsb200_report_t *report);
 
+/* The same with everything the device API offers: this rank's shard of a sharded vector (comm != NULL) and an
+ * optional fused trial evaluate.  x_host should be pinned memory for full PCIe speed. */
+int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, int64_t n_local, int64_t n_global,
+                               int64_t global_offset, int device, lbfgsb200_comm_t *comm, lbfgsb200_eval_fn eval,
+                               void *eval_user, lbfgsb200_trial_eval_fn trial_eval, void *trial_user,
+                               lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 enum {
     LBFGSB200_K_DOTS = 0,       /* {g.d, g.g, x.x} in one read                       src/core.rs:114-116,183-194 */

@@ -123,6 +123,7 @@ def lib():
     _sig(L, "lbfgsb200_gx", vp, [vp])
     _sig(L, "lbfgsb200_direction", vp, [vp])
     _sig(L, "lbfgsb200_minimize_host", i32, [pp(Param), vp, i64, i32, vp, vp, vp, vp, pp(Report)])
+    _sig(L, "lbfgsb200_minimize_host_ex", i32, [pp(Param), vp, i64, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, pp(Report)])
     _sig(L, "lbfgsb200_profile_enable", i32, [vp, i32])
     _sig(L, "lbfgsb200_profile_get", i32, [vp, pp(Profile)])
     _sig(L, "lbfgsb200_profile_reset", i32, [vp])

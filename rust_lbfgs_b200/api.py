@@ -310,6 +310,41 @@ class Lbfgs:
             L.lbfgsb200_destroy(solver)
 
 
+    def minimize_host(self, x_host, evaluate, progress=None, device=0):
+        """The reference's exact call shape: `x` is a HOST slice (`minimize(&mut x, ..)`, src/lbfgs.rs:399) — a
+        float64 numpy array or CPU tensor, updated in place.  One C-ABI call (lbfgsb200_minimize_host_ex) copies it
+        to the device, solves there and copies the result back.  Pinned memory gives full PCIe speed."""
+        L = _lib.lib()
+        if hasattr(x_host, "data_ptr"):
+            if x_host.is_cuda or str(x_host.dtype) != "torch.float64" or not x_host.is_contiguous():
+                raise ValueError("x_host must be a contiguous float64 CPU tensor")
+            ptr, n = int(x_host.data_ptr()), int(x_host.numel())
+        else:
+            import numpy as np
+            if not (isinstance(x_host, np.ndarray) and x_host.dtype == np.float64 and x_host.flags.c_contiguous):
+                raise ValueError("x_host must be a C-contiguous float64 numpy array")
+            ptr, n = int(x_host.ctypes.data), int(x_host.size)
+        n_global, goff = (n, 0) if self._shard is None else self._shard
+        comm = self._comm._handle if self._comm is not None else None
+        ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial)
+        cb = cbp = None
+        if progress is not None:
+            def on_progress(_user, pp):
+                return 1 if progress(_progress_from_c(pp.contents, device)) else 0
+            cb = PROGRESS_FN(on_progress)
+            cbp = C.cast(cb, C.c_void_p)
+        rep = _lib.Report()
+        st = L.lbfgsb200_minimize_host_ex(C.byref(self.param), ptr, n, n_global, goff, device, comm, ev.fn, ev.user,
+                                          ev.trial_fn, ev.user if ev.trial_fn else None, cbp, None, C.byref(rep))
+        report = _report_from_c(rep)
+        report.status = st
+        if st == -5:
+            raise ValueError("invalid L-BFGS parameter (the reference would panic)")
+        if st < 0:
+            raise LbfgsError(st, f"minimize_host failed with status {STATUS_NAMES.get(st, st)}", report)
+        return report
+
+
 def lbfgs():
     """Create a default LBFGS optimizer (src/lib.rs:74-76)."""
     return Lbfgs()

@@ -1,7 +1,10 @@
 // capi.cpp — the extern "C" surface declared in include/lbfgsb200.h.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -152,31 +155,60 @@ const double *lbfgsb200_x(const lbfgsb200_solver_t *solver) { return solver ? S(
 const double *lbfgsb200_gx(const lbfgsb200_solver_t *solver) { return solver ? S(solver)->gx() : nullptr; }
 const double *lbfgsb200_direction(const lbfgsb200_solver_t *solver) { return solver ? S(solver)->direction() : nullptr; }
 
-int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int64_t n, int device,
-                            lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
-                            void *progress_user, lbfgsb200_report_t *report) {
-    if (!param || !x_host || n < 1 || !eval) return LBFGSB200_ERR_INVALID_PARAM;
+int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, int64_t n_local, int64_t n_global,
+                               int64_t global_offset, int device, lbfgsb200_comm_t *comm, lbfgsb200_eval_fn eval,
+                               void *eval_user, lbfgsb200_trial_eval_fn trial_eval, void *trial_user,
+                               lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report) {
+    if (!param || !x_host || n_local < 1 || !eval) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    const char *dbg_env = getenv("LBFGSB200_DEBUG_TIMING");
+    const bool dbg = dbg_env && dbg_env[0] != '0';
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!dbg) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lbfgsb200] minimize_host: %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     cudaStream_t stream = nullptr;
     if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    lap("stream create");
     double *x_dev = nullptr;
     int status = LBFGSB200_ERR_CUDA;
     lbfgsb200_solver_t *solver = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)n_local;
     do {
-        if (cudaMalloc((void **)&x_dev, sizeof(double) * (size_t)n) != cudaSuccess) break;
-        if (cudaMemcpyAsync(x_dev, x_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, stream) != cudaSuccess) break;
-        status = lbfgsb200_create(param, n, n, 0, device, stream, nullptr, &solver);
+        // the arena first: it is the big block a previous solve left in the pool; x then takes a small one
+        status = lbfgsb200_create(param, n_local, n_global, global_offset, device, stream, comm, &solver);
         if (status != 0) break;
+        lap("solver create");
+        status = LBFGSB200_ERR_CUDA;
+        x_dev = S(solver)->spare_x();   // the device copy of x lives in the solver's (pooled) arena
+        if (cudaMemcpyAsync(x_dev, x_host, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) break;
+        lap("H2D enqueue");
+        if (trial_eval) lbfgsb200_set_trial_evaluate(solver, trial_eval, trial_user);
         status = lbfgsb200_minimize(solver, x_dev, eval, eval_user, progress, progress_user, report);
-        if (cudaMemcpyAsync(x_host, x_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        lap("minimize");
+        if (cudaMemcpyAsync(x_host, x_dev, bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
             cudaStreamSynchronize(stream) != cudaSuccess) {
             if (status >= 0) status = LBFGSB200_ERR_CUDA;
         }
+        lap("D2H + sync");
     } while (0);
+    x_dev = nullptr;
     if (solver) lbfgsb200_destroy(solver);
-    if (x_dev) cudaFree(x_dev);
+    lap("solver destroy");
+    cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
+    lap("stream destroy");
     return status;
+}
+
+int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int64_t n, int device,
+                            lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
+                            void *progress_user, lbfgsb200_report_t *report) {
+    return lbfgsb200_minimize_host_ex(param, x_host, n, n, 0, device, nullptr, eval, eval_user, nullptr, nullptr, progress,
+                                      progress_user, report);
 }
 
 int lbfgsb200_profile_enable(lbfgsb200_solver_t *solver, int timing) {

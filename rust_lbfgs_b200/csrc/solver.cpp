@@ -239,9 +239,13 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
 
-    // One arena for every owned vector: x', g, gp, d, [pg], S[m], Y[m], [wp]
+    // One arena for every owned vector: x', g, gp, d, [pg], S[m], Y[m], one spare vector, [wp].  The spare is the
+    // device copy of x for the host-buffer entry points (lbfgsb200_minimize_host*): keeping it inside the arena
+    // makes every solver of the same (n, m) ask the memory pool for the same block size, so host-API and
+    // device-API solves recycle each other's arena instead of going to the driver (whose physical allocations
+    // of even 0.8 GB were measured at 5 .. 640 ms on these boxes).
     const int64_t vec_bytes = round_up(n_ * (int64_t)sizeof(double), kAlign);
-    const int64_t nvec = 4 + (owl_ ? 1 : 0) + 2 * m_;
+    const int64_t nvec = 4 + (owl_ ? 1 : 0) + 2 * m_ + 1;
     const int64_t wp_bytes = owl_ ? round_up(n_, kAlign) : 0;
     arena_pooled_ = use_pool(device);
     if (arena_pooled_) e = cudaMallocAsync(&arena_, (size_t)(nvec * vec_bytes + wp_bytes), stream_);
@@ -258,6 +262,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     S_.resize(m_);
     Y_.resize(m_);
     for (int64_t i = 0; i < m_; ++i) { S_[i] = take(); Y_[i] = take(); }
+    x_spare_ = take();
     if (owl_) wp_ = (signed char *)base;
 
     const size_t scal_need = SLOT_COUNT * kMaxAcc + 2 * (size_t)m_;   // slots, alpha[m], ys[m]
@@ -277,7 +282,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     tm.lap("create: scalars + pinned + workspace");
 
     // evict-first accesses once the working set cannot live in L2
-    const double working_set = (double)(nvec + 1) * (double)vec_bytes;
+    const double working_set = (double)nvec * (double)vec_bytes;
     streaming_ = working_set > 0.75 * (double)dev_.l2_bytes;
     const int force = env_int("LBFGSB200_STREAMING", -1);
     if (force == 0) streaming_ = false;

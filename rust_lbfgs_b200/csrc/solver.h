@@ -63,6 +63,7 @@ class Solver {
     const double *x() const { return xbuf_[cur_x_]; }
     const double *gx() const { return gbuf_[cur_g_]; }
     const double *direction() const { return d_; }
+    double *spare_x() const { return x_spare_; }   // an n-vector of the arena for the host-buffer entry points
     const std::string &error() const { return err_; }
 
     // optional fused trial evaluate (lbfgsb200_trial_eval_fn); ignored for OWL-QN
@@ -119,7 +120,7 @@ class Solver {
     bool arena_pooled_ = false;             // cudaMallocAsync from the device's default pool
     double *xbuf_[2] = {nullptr, nullptr};  // [0] = caller's x, [1] = ours
     double *gbuf_[2] = {nullptr, nullptr};
-    double *d_ = nullptr, *pg_ = nullptr;
+    double *d_ = nullptr, *pg_ = nullptr, *x_spare_ = nullptr;
     signed char *wp_ = nullptr;
     std::vector<double *> S_, Y_;
     double *scal_dev_ = nullptr;    // SLOT_COUNT * kMaxAcc doubles, then alpha[m]

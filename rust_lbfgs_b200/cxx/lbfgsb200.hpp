@@ -208,8 +208,12 @@ class Lbfgs {
     Report minimize(std::vector<double> &x, const Objective &objective, ProgressFn progress = nullptr) const {
         lbfgsb200_report_t rep{};
         lbfgsb200_objective_set_reduction(objective.handle(), (int)p_.reduction);
-        int st = lbfgsb200_minimize_host(&p_, x.data(), (int64_t)x.size(), device_, lbfgsb200_objective_eval, objective.handle(),
-                                         progress ? tramp_progress : nullptr, progress ? &progress : nullptr, &rep);
+        const bool fused = fused_ && lbfgsb200_objective_has_trial_eval(objective.handle());
+        const int64_t n = (int64_t)x.size();
+        int st = lbfgsb200_minimize_host_ex(&p_, x.data(), n, n_global_ > 0 ? n_global_ : n, goff_, device_, comm_,
+                                            lbfgsb200_objective_eval, objective.handle(),
+                                            fused ? lbfgsb200_objective_trial_eval : nullptr, fused ? objective.handle() : nullptr,
+                                            progress ? tramp_progress : nullptr, progress ? &progress : nullptr, &rep);
         Report r = convert(rep, st);
         if (st < 0) throw Error(st, "minimize failed (status " + std::to_string(st) + ")", r);
         return r;

@@ -137,6 +137,10 @@ extern "C" {
                                    eval_user: *mut c_void, progress: lbfgsb200_progress_fn, progress_user: *mut c_void,
                                    report: *mut lbfgsb200_report_t) -> c_int;
 
+    pub fn lbfgsb200_minimize_host_ex(param: *const lbfgsb200_param_t, x_host: *mut f64, n_local: i64, n_global: i64, global_offset: i64,
+                                      device: c_int, comm: *mut lbfgsb200_comm_t, eval: lbfgsb200_eval_fn, eval_user: *mut c_void,
+                                      trial_eval: lbfgsb200_trial_eval_fn, trial_user: *mut c_void, progress: lbfgsb200_progress_fn,
+                                      progress_user: *mut c_void, report: *mut lbfgsb200_report_t) -> c_int;
     pub fn lbfgsb200_profile_enable(solver: *mut lbfgsb200_solver_t, timing: c_int) -> c_int;
     pub fn lbfgsb200_profile_get(solver: *mut lbfgsb200_solver_t, out: *mut lbfgsb200_profile_t) -> c_int;
     pub fn lbfgsb200_profile_reset(solver: *mut lbfgsb200_solver_t) -> c_int;

@@ -208,6 +208,22 @@ def test_error_paths_match_reference_semantics(oracle):
     assert got["status_name"] == "ERR_EVALUATE"
 
 
+def test_minimize_host_slice_like_the_reference(oracle):
+    """`minimize(&mut x, ..)` with x a HOST slice (src/lbfgs.rs:399): one C-ABI call, x updated in place."""
+    ref = oracle_run(oracle, rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"))
+    x = rosenbrock_x0(100)
+    trace = []
+    rep = R.lbfgs().minimize_host(x, R.Rosenbrock(), lambda p: trace.append((p.niter, p.ncall)) and False)
+    assert rep.status_name == "OK_CONVERGED" and rep.neval == ref["report"]["neval"] and len(trace) == len(ref["trace"])
+    assert np.max(np.abs(x - ref["x"])) <= 1e-8 and abs(rep.fx) <= 1e-4
+    import torch
+    xt = torch.tensor(rosenbrock_x0(1000)).pin_memory()
+    rep = R.lbfgs().with_max_iterations(20).with_fused_trial(False).minimize_host(xt, R.Rosenbrock())
+    assert rep.status_name == "OK_MAX_ITERATIONS" and rep.niter == 20
+    with pytest.raises(ValueError):
+        R.lbfgs().minimize_host(np.zeros(4, dtype=np.float32), R.Rosenbrock())
+
+
 def test_iterative_api_matches_minimize(oracle):
     """build / is_converged / propagate / report (src/lbfgs.rs:443-566)."""
     import torch
