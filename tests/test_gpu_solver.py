@@ -11,6 +11,7 @@ drift apart by more than tol/100 — L-BFGS amplifies last-bit differences of th
 tolerance is widened to 100x that measured drift (gpu_util.compare_traces); counts must still match
 exactly whenever the two CPU orders agree with each other."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -311,3 +312,29 @@ def test_full_size_invariants_n1e8():
             assert p.fx < fx_prev
         fx_prev = p.fx
     st.close()
+
+
+def test_examples_run_like_the_reference(capsys):
+    """examples/sample.rs (device and host shapes) and examples/lj.rs."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    sample = load("sample")
+    argv = sys.argv
+    try:
+        sys.argv = ["sample.py"]
+        a = sample.main()
+        sys.argv = ["sample.py", "--host"]
+        b = sample.main()
+    finally:
+        sys.argv = argv
+    assert a.status_name == b.status_name == "OK_CONVERGED" and a.neval == b.neval == 40 and abs(a.fx) < 1e-4
+    rep = load("lj").main()
+    assert rep.status_name == "OK_CONVERGED" and rep.fx < -160.0
+    out = capsys.readouterr().out
+    assert "Iteration 35:" in out and "Evaluation:" in out
