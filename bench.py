@@ -146,6 +146,31 @@ def cpu_oracle_rate(n_sample, warmup, steps, m=6, budget_s=None):
     return done / dt, dt, done
 
 
+def isometric_oracle_trace(n_global, m, iters):
+    """The reference algorithm (oracle) on the n = 1e8 workload WITHOUT summation error: with x0 = (-1.2, 1) repeated
+    every pair of the vector is identical for ever, so the solve lives in a 2-dimensional subspace; u = sqrt(n/2) x
+    is an isometry from that subspace to R^2, and the reference solver run on F(u) = (n/2) f(u / sqrt(n/2)) follows
+    the same trajectory (same dot products, same line-search decisions).  Checked against the real oracle at
+    n = 100, 1e5 and 2e6 (identical evaluation counts over 51 iterations, x to 3e-12).  Used as the CHECKER of the
+    timed run: the CUDA path must take the same number of evaluations in every iteration and see the same f."""
+    import math
+    import numpy as np
+    from oracle import oracle_lib as O
+    K = n_global // 2
+    rK = math.sqrt(K)
+
+    def f(u, g):
+        x0, x1 = u[0] / rK, u[1] / rK
+        t1 = 1.0 - x0
+        t2 = 10.0 * (x1 - x0 * x0)
+        g1 = 20.0 * t2
+        g0 = -2.0 * (x0 * g1 + t1)
+        g[0], g[1] = rK * g0, rK * g1
+        return K * (t1 * t1 + t2 * t2)
+    r = O.minimize(O.default_param(m=m, max_iterations=iters), np.array([-1.2 * rK, 1.0 * rK]), O.Objective.python(f))
+    return r["trace"]
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the path.  The reference is Rust and this
     image has no rustc/cargo, so it is the oracle port (oracle/lbfgs_oracle.cpp), single-threaded like the
@@ -235,10 +260,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     wall_begin = time.time()
     ev0.record()
-    ncalls = []
+    ncalls, seen = [], []
     for _ in range(K):
         p = state.propagate()
         ncalls.append(p.ncall)
+        seen.append((p.niter, p.ncall, p.fx, p.xnorm, p.gnorm, p.step))
     ev1.record()
     torch.cuda.synchronize()
     wall_end = time.time()
@@ -327,6 +353,26 @@ def run_ours(args):
     }
     del xh
 
+    # ---- the timed trajectory against the reference algorithm (checker only; rank 0) -------------------------
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline and n_global % 2 == 0:
+        try:
+            ref = {t["niter"]: t for t in isometric_oracle_trace(n_global, m, 1 + W + K)}
+            worst = 0.0
+            same = True
+            for (it, nc, fx, xn, gn, stp) in seen:
+                t = ref.get(it)
+                if t is None or t["ncall"] != nc:
+                    same = False
+                    break
+                for a, b in ((fx, t["fx"]), (xn, t["xnorm"]), (gn, t["gnorm"]), (stp, t["step"])):
+                    worst = max(worst, abs(a - b) / max(abs(b), 1e-300))
+            parity = {"checker": "oracle on the isometric 2-variable image of the workload (bench.py: isometric_oracle_trace)",
+                      "iterations_checked": len(seen), "evaluations_per_iteration_identical": same,
+                      "max_rel_err_fx_xnorm_gnorm_step": worst}
+        except Exception as e:  # the checker must never break the measurement
+            parity = {"error": repr(e)}
+
     # ---- the reference's CPU path on this host (rank 0, N=1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -348,7 +394,7 @@ def run_ours(args):
                        "n_per_gpu": n_local, "n_global": n_global, "m": m, "linesearch": "MoreThuente",
                        "l2_policy": "inputs larger than L2 (19 vectors x 0.8 GB vs 126 MB)",
                        "ncall_per_iteration": ncalls, "final_fx": final.fx, "final_gnorm": final.gnorm},
-            "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
             "gpu_launches": gpu_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -338,3 +338,31 @@ def test_examples_run_like_the_reference(capsys):
     assert rep.status_name == "OK_CONVERGED" and rep.fx < -160.0
     out = capsys.readouterr().out
     assert "Iteration 35:" in out and "Evaluation:" in out
+
+
+def test_full_size_n1e8_follows_the_reference_algorithm(oracle):
+    """50 iterations at n = 1e8 against the reference algorithm.  The real oracle cannot serve here (its sequential
+    sums are off by 1e-9 at this size), but with identical pairs the solve is confined to a 2-dimensional subspace
+    and u = sqrt(n/2) x maps it isometrically to R^2 (bench.isometric_oracle_trace): same dot products, same
+    line-search decisions.  The CUDA path must use the same number of evaluations in EVERY iteration and agree in
+    fx, ||x||, ||g|| and step to 1e-9."""
+    import torch
+    import bench
+    n, iters = 100_000_000, 51
+    free, _ = torch.cuda.mem_get_info()
+    if free < 20 * 8 * n * 1.05:
+        pytest.skip("not enough free HBM")
+    ref = bench.isometric_oracle_trace(n, 6, iters)
+    x = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    x[0::2] = -1.2
+    x[1::2] = 1.0
+    st = R.lbfgs().build(x, R.Rosenbrock())
+    worst = 0.0
+    for t in ref:
+        p = st.propagate()
+        assert (p.niter, p.neval, p.ncall) == (t["niter"], t["neval"], t["ncall"]), (t["niter"], p.ncall, t["ncall"])
+        for a, b in ((p.fx, t["fx"]), (p.xnorm, t["xnorm"]), (p.gnorm, t["gnorm"]), (p.step, t["step"])):
+            worst = max(worst, abs(a - b) / abs(b))
+    st.close()
+    print("worst relative deviation over", len(ref), "iterations:", worst)
+    assert len(ref) == iters and worst <= 1e-9
