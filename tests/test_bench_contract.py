@@ -41,3 +41,24 @@ def test_survey_formula_bytes():
     kbytes = {"backward": 23.0 * V, "forward": 24.0 * V}   # b = 6: (8b - 1) V
     # (6t + 6 + 8b) V + 2 V t with t = 3, b = 6  ->  8tV + 7V + 47V
     assert bench.algorithmic_bytes_survey(n, launches, kbytes) == (8 * 3 + 7 + 47) * V
+
+
+def test_isometric_oracle_is_the_reference_algorithm(oracle):
+    """bench.isometric_oracle_trace (the checker of the timed n = 1e8 run) against the real oracle where that is
+    feasible: identical evaluation counts in every iteration, fx / norms / step to 1e-9."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    for n, mode in ((100, 0), (10_000, 0), (400_000, 1)):
+        x0 = np.zeros(n)
+        x0[0::2], x0[1::2] = -1.2, 1.0
+        real = oracle.minimize(oracle.default_param(max_iterations=51, reduction_mode=mode), x0,
+                               oracle.Objective.builtin("rosenbrock", mode))["trace"]
+        iso = bench.isometric_oracle_trace(n, 6, 51)
+        assert len(real) == len(iso)
+        for a, b in zip(real, iso):
+            assert (a["niter"], a["neval"], a["ncall"]) == (b["niter"], b["neval"], b["ncall"])
+            for k in ("fx", "xnorm", "gnorm", "step"):
+                # relative to the value, with a floor at 1e-12 of its starting magnitude (near convergence fx and
+                # ||g|| are differences of O(1) quantities)
+                assert abs(a[k] - b[k]) <= 1e-9 * abs(a[k]) + 1e-12 * abs(real[0][k]), (n, a["niter"], k, a[k], b[k])
