@@ -59,6 +59,6 @@ def test_isometric_oracle_is_the_reference_algorithm(oracle):
         for a, b in zip(real, iso):
             assert (a["niter"], a["neval"], a["ncall"]) == (b["niter"], b["neval"], b["ncall"])
             for k in ("fx", "xnorm", "gnorm", "step"):
-                # relative to the value, with a floor at 1e-12 of its starting magnitude (near convergence fx and
+                # relative to the value, with a floor at 1e-9 of its starting magnitude (near convergence fx and
                 # ||g|| are differences of O(1) quantities)
-                assert abs(a[k] - b[k]) <= 1e-8 * abs(a[k]) + 1e-12 * abs(real[0][k]), (n, a["niter"], k, a[k], b[k])
+                assert abs(a[k] - b[k]) <= 1e-8 * abs(a[k]) + 1e-9 * abs(real[0][k]), (n, a["niter"], k, a[k], b[k])
