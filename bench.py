@@ -146,7 +146,7 @@ def cpu_oracle_rate(n_sample, warmup, steps, m=6, budget_s=None):
     return done / dt, dt, done
 
 
-def isometric_oracle_trace(n_global, m, iters):
+def isometric_oracle_trace(n_global, m, iters, owl_c=None, record_x=False):
     """The reference algorithm (oracle) on the n = 1e8 workload WITHOUT summation error: with x0 = (-1.2, 1) repeated
     every pair of the vector is identical for ever, so the solve lives in a 2-dimensional subspace; u = sqrt(n/2) x
     is an isometry from that subspace to R^2, and the reference solver run on F(u) = (n/2) f(u / sqrt(n/2)) follows
@@ -167,7 +167,14 @@ def isometric_oracle_trace(n_global, m, iters):
         g0 = -2.0 * (x0 * g1 + t1)
         g[0], g[1] = rK * g0, rK * g1
         return K * (t1 * t1 + t2 * t2)
-    r = O.minimize(O.default_param(m=m, max_iterations=iters), np.array([-1.2 * rK, 1.0 * rK]), O.Objective.python(f))
+    kw = {}
+    if owl_c is not None:   # c * sum |x_i| = c sqrt(n/2) (|u_0| + |u_1|): OWL-QN on all of x maps to OWL-QN on u
+        kw = dict(orthantwise=1, owl_c=owl_c * rK, owl_start=0, owl_end=-1)
+    r = O.minimize(O.default_param(m=m, max_iterations=iters, **kw), np.array([-1.2 * rK, 1.0 * rK]), O.Objective.python(f),
+                   record_x=record_x)
+    if record_x:
+        for t in r["trace"]:
+            t["x_pair"] = (t["x"][0] / rK, t["x"][1] / rK)
     return r["trace"]
 
 

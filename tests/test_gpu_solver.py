@@ -366,3 +366,33 @@ def test_full_size_n1e8_follows_the_reference_algorithm(oracle):
     st.close()
     print("worst relative deviation over", len(ref), "iterations:", worst)
     assert len(ref) == iters and worst <= 1e-9
+
+
+def test_full_size_owlqn_n1e8_follows_the_reference_algorithm(oracle):
+    """OWL-QN (c = 2 on all of x) at n = 1e8 against the isometric oracle (c sum|x_i| = c sqrt(n/2) sum|u_j|): same
+    evaluations in every iteration, fx and norms to 1e-9, and the same orthant sign pattern of x in every iterate."""
+    import torch
+    import bench
+    n, iters, c = 100_000_000, 41, 2.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 21 * 8 * n * 1.05:
+        pytest.skip("not enough free HBM")
+    ref = bench.isometric_oracle_trace(n, 6, iters, owl_c=c, record_x=True)
+    x = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    x[0::2] = -1.2
+    x[1::2] = 1.0
+    st = R.lbfgs().with_orthantwise(c, 0).build(x, R.Rosenbrock())
+    worst = 0.0
+    for t in ref:
+        p = st.propagate()
+        assert (p.niter, p.neval, p.ncall) == (t["niter"], t["neval"], t["ncall"]), (t["niter"], p.ncall, t["ncall"])
+        for a, b in ((p.fx, t["fx"]), (p.xnorm, t["xnorm"]), (p.gnorm, t["gnorm"])):
+            worst = max(worst, abs(a - b) / abs(b))
+        pair = p.x[:2].cpu().numpy()
+        assert np.array_equal(np.sign(pair), np.sign(np.array(t["x_pair"]))), (t["niter"], pair, t["x_pair"])
+        assert np.max(np.abs(pair - np.array(t["x_pair"]))) <= 1e-9
+        last = p.x[-2:].cpu().numpy()
+        assert np.array_equal(last, pair)            # every pair still identical (the premise of the isometry)
+    st.close()
+    print("OWL-QN n=1e8: worst relative deviation over", len(ref), "iterations:", worst)
+    assert len(ref) == iters and worst <= 1e-9
