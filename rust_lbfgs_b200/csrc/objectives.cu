@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(kThreads) k_glm_grad_final(const double *__res
 // ---- GLM, fused: ONE pass over X ---------------------------------------------------------------------
 // z_r = X[r,:].w, the per-row loss term and residual t_r, and the gradient update g += t_r X[r,:] all while
 // row r is on chip, so X (80 GB at 1e6 x 1e4) crosses HBM once per evaluation instead of twice.
-//   * one 256-thread CTA per SM owns rows r = blockIdx.x, + gridDim.x, ...
-//   * rows are staged in shared memory by 1-D TMA bulk copies (cp.async.bulk -> mbarrier complete_tx), a ring
-//     of `stages` row buffers so the next rows are in flight while this one is consumed (2 stages of 80 KB at
+//   * one 256-thread CTA per SM owns row groups g = blockIdx.x, + gridDim.x, ... of R consecutive rows
+//     (R = 1 for 80 KB rows, up to 8 for short ones: ~64 KB per group, so the two block barriers per group
+//     are amortised);
+//   * groups are staged in shared memory by 1-D TMA bulk copies (cp.async.bulk -> mbarrier complete_tx), a ring
+//     of `stages` buffers so the next groups are in flight while this one is consumed (2 stages of 80 KB at
 //     ncol = 1e4, more for shorter rows);
 //   * every thread owns KP fixed column pairs: its slice of w and its slice of the gradient accumulator live in
 //     registers for the whole kernel; the row is read from shared memory twice (dot, then axpy);
@@ -223,18 +225,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 constexpr int kGlmMaxStages = 8;
 constexpr uint32_t kTmaChunk = 32768;  // bytes per bulk copy
 
-template <int KP>
+// KP column pairs per thread, R consecutive rows per pipeline stage.  Short rows (ncol of a few thousand) cannot
+// pay two block barriers each — a 16 KB row lasts 0.36 us at this SM's share of the HBM bandwidth — so a stage
+// holds R rows (they are contiguous in X: one bulk copy), the R dot products are reduced together and the R
+// rank-one updates applied together.
+template <int KP, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const double *__restrict__ w,
-            double *__restrict__ gpart, int64_t nrow, int64_t ncol, int kind, int stages, uint32_t row_stride,
+            double *__restrict__ gpart, int64_t nrow, int64_t ncol, int kind, int stages, uint32_t stage_stride,
             ReduceWs ws, double *fx) {
     extern __shared__ __align__(128) unsigned char glm_smem[];
     __shared__ __align__(8) uint64_t full_bar[kGlmMaxStages];
-    __shared__ double red[2][kWarps];
+    __shared__ double red[2][R][kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t npairs = ncol >> 1;
     const uint32_t row_bytes = (uint32_t)(ncol * 8);
-    const int64_t my_rows = (nrow > (int64_t)blockIdx.x) ? (nrow - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t ngroups = (nrow + R - 1) / R;      // groups of R rows; the last one may be short
+    const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     double2 wv[KP], gv[KP];
 #pragma unroll
@@ -243,15 +250,21 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
         wv[k] = (p < npairs) ? reinterpret_cast<const double2 *>(w)[p] : make_double2(0.0, 0.0);
         gv[k] = make_double2(0.0, 0.0);
     }
-    auto issue = [&](int64_t i) {  // thread 0: stage row i of this CTA
+    auto rows_in = [&](int64_t i) {  // rows of this CTA's i-th group
+        const int64_t r0 = (blockIdx.x + i * gridDim.x) * R;
+        return (int)((nrow - r0 < R) ? (nrow - r0) : R);
+    };
+    auto issue = [&](int64_t i) {  // thread 0: stage group i of this CTA
         const int s = (int)(i % stages);
-        const double *src = X + (blockIdx.x + i * gridDim.x) * ncol;
-        unsigned char *dst = glm_smem + (size_t)s * row_stride;
+        const int64_t r0 = (blockIdx.x + i * gridDim.x) * R;
+        const uint32_t bytes = row_bytes * (uint32_t)rows_in(i);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(X + r0 * ncol);
+        unsigned char *dst = glm_smem + (size_t)s * stage_stride;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer
-        mbar_expect_tx(&full_bar[s], row_bytes);
-        for (uint32_t off = 0; off < row_bytes; off += kTmaChunk) {
-            const uint32_t nb = (row_bytes - off < kTmaChunk) ? (row_bytes - off) : kTmaChunk;
-            tma_load_1d(dst + off, reinterpret_cast<const unsigned char *>(src) + off, nb, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], bytes);
+        for (uint32_t off = 0; off < bytes; off += kTmaChunk) {
+            const uint32_t nb = (bytes - off < kTmaChunk) ? (bytes - off) : kTmaChunk;
+            tma_load_1d(dst + off, src + off, nb, &full_bar[s]);
         }
     };
     if (tid == 0) {
@@ -260,63 +273,85 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
     }
     __syncthreads();
     if (tid == 0)
-        for (int64_t i = 0; i < stages && i < my_rows; ++i) issue(i);
+        for (int64_t i = 0; i < stages && i < my_groups; ++i) issue(i);
 
-    double facc = 0.0;
-    double y_next = (my_rows > 0 && lane == 0) ? y[blockIdx.x] : 0.0;
-    for (int64_t i = 0; i < my_rows; ++i) {
+    double facc = 0.0;   // lanes 0..R-1 of warp 0 accumulate the loss terms of "their" row of every group
+    auto load_y = [&](int64_t i) {
+        const int64_t r = (blockIdx.x + i * gridDim.x) * R + lane;
+        return (lane < R && i < my_groups && r < nrow) ? y[r] : 0.0;
+    };
+    double y_next = load_y(0);
+    for (int64_t i = 0; i < my_groups; ++i) {
         const int s = (int)(i % stages);
         const uint32_t parity = (uint32_t)((i / stages) & 1);
+        const int nr = (R == 1) ? 1 : rows_in(i);   // R == 1: every group is one full row (compile-time)
         const double yr = y_next;
-        if (lane == 0 && i + 1 < my_rows) y_next = y[blockIdx.x + (i + 1) * gridDim.x];
+        y_next = load_y(i + 1);
         mbar_wait(&full_bar[s], parity);
-        const double2 *row = reinterpret_cast<const double2 *>(glm_smem + (size_t)s * row_stride);
-        double part = 0.0;
+        const unsigned char *stage = glm_smem + (size_t)s * stage_stride;
+        double part[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) part[r] = 0.0;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const int64_t p = tid + (int64_t)k * kThreads;
             if (p < npairs) {
-                const double2 xv = row[p];
-                part += wv[k].x * xv.x;
-                part += wv[k].y * xv.y;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < nr) {
+                        const double2 xv = reinterpret_cast<const double2 *>(stage + (size_t)r * row_bytes)[p];
+                        part[r] += wv[k].x * xv.x;
+                        part[r] += wv[k].y * xv.y;
+                    }
+                }
             }
         }
-        part = warp_sum(part);
-        if (lane == 0) red[i & 1][warp] = part;
-        __syncthreads();
-        double z = 0.0;
 #pragma unroll
-        for (int q = 0; q < kWarps; ++q) z += red[i & 1][q];
-        double t = 0.0;
-        if (lane == 0) {  // one lane per warp evaluates the link function; f is accumulated once per CTA
+        for (int r = 0; r < R; ++r) {
+            const double v = warp_sum(part[r]);
+            if (lane == 0) red[i & 1][r][warp] = v;
+        }
+        __syncthreads();
+        // lane r of every warp finishes row r: z, the link function, t; warp 0 also books the loss term
+        double t_mine = 0.0;
+        if (lane < nr) {
+            double z = 0.0;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) z += red[i & 1][lane][q];
             double term;
             if (kind == 0) {
                 const double e = exp(z);
                 term = yr * z - e;
-                t = yr - e;
+                t_mine = -(yr - e);                       // g = (-X^T) t, tests/owlqn.rs:40
             } else {
                 const double sp = fmax(z, 0.0) + log1p(exp(-fabs(z)));
                 double mu;
                 if (z >= 0.0) mu = 1.0 / (1.0 + exp(-z));
                 else { const double e = exp(z); mu = e / (1.0 + e); }
                 term = sp - yr * z;
-                t = mu - yr;
+                t_mine = mu - yr;
             }
             if (warp == 0) facc += term;
         }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (kind == 0) t = -t;  // g = (-X^T) t, tests/owlqn.rs:40
+        double t[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r] = __shfl_sync(0xffffffffu, t_mine, r);
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const int64_t p = tid + (int64_t)k * kThreads;
             if (p < npairs) {
-                const double2 xv = row[p];
-                gv[k].x += t * xv.x;
-                gv[k].y += t * xv.y;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r < nr) {
+                        const double2 xv = reinterpret_cast<const double2 *>(stage + (size_t)r * row_bytes)[p];
+                        gv[k].x += t[r] * xv.x;
+                        gv[k].y += t[r] * xv.y;
+                    }
+                }
             }
         }
         __syncthreads();  // every thread is done with stage s: it may be refilled
-        if (tid == 0 && i + stages < my_rows) issue(i + stages);
+        if (tid == 0 && i + stages < my_groups) issue(i + stages);
     }
     double *gp = gpart + (int64_t)blockIdx.x * ncol;
 #pragma unroll
@@ -328,40 +363,51 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
     grid_reduce<1>(acc, ws, fx);
 }
 
-template <int KP>
+template <int KP, int R>
 int launch_glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
     const uint32_t row_bytes = (uint32_t)(o->ncol * 8);
-    const uint32_t row_stride = (row_bytes + 127u) & ~127u;
-    int stages = (int)((200u * 1024u) / row_stride);
+    const uint32_t stage_stride = (row_bytes * (uint32_t)R + 127u) & ~127u;
+    int stages = (int)((200u * 1024u) / stage_stride);
     if (stages > kGlmMaxStages) stages = kGlmMaxStages;
     if (stages < 2) return LBFGSB200_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * row_stride;
+    const size_t smem = (size_t)stages * stage_stride;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_glm_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_glm_fused<KP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return LBFGSB200_ERR_CUDA;
         attr_set = true;
     }
+    const int64_t ngroups = (o->nrow + R - 1) / R;
     int grid = o->dev.sm_count;
-    if ((int64_t)grid > o->nrow) grid = (int)o->nrow;
-    k_glm_fused<KP><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind, stages,
-                                                       row_stride, o->ws, fx);
+    if ((int64_t)grid > ngroups) grid = (int)ngroups;
+    k_glm_fused<KP, R><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind, stages,
+                                                          stage_stride, o->ws, fx);
     const unsigned cb = (unsigned)((o->ncol + kThreads - 1) / kThreads);
     k_glm_grad_final<<<cb, kThreads, 0, stream>>>(o->gfused, g, o->ncol, grid);
     return 0;
+}
+
+// rows per stage: enough for ~32-64 KB per stage (R * 16 B-aligned rows are contiguous in X)
+template <int KP>
+int launch_glm_fused_r(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
+    const int64_t row_bytes = o->ncol * 8;
+    if (row_bytes * 8 <= 65536) return launch_glm_fused<KP, 8>(o, w, g, stream, fx);
+    if (row_bytes * 4 <= 65536) return launch_glm_fused<KP, 4>(o, w, g, stream, fx);
+    if (row_bytes * 2 <= 65536) return launch_glm_fused<KP, 2>(o, w, g, stream, fx);
+    return launch_glm_fused<KP, 1>(o, w, g, stream, fx);
 }
 
 // 0 = launched; LBFGSB200_ERR_UNSUPPORTED = shape not covered (caller falls back to the two-pass kernels)
 int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
     if (!o->gfused || (o->ncol & 1) || (((uintptr_t)o->X | (uintptr_t)w) & 15u)) return LBFGSB200_ERR_UNSUPPORTED;
     const int64_t need = (o->ncol / 2 + kThreads - 1) / kThreads;  // column pairs per thread
-    if (need <= 1) return launch_glm_fused<1>(o, w, g, stream, fx);
-    if (need <= 2) return launch_glm_fused<2>(o, w, g, stream, fx);
-    if (need <= 4) return launch_glm_fused<4>(o, w, g, stream, fx);
-    if (need <= 8) return launch_glm_fused<8>(o, w, g, stream, fx);
-    if (need <= 12) return launch_glm_fused<12>(o, w, g, stream, fx);
-    if (need <= 16) return launch_glm_fused<16>(o, w, g, stream, fx);
-    if (need <= 20) return launch_glm_fused<20>(o, w, g, stream, fx);
+    if (need <= 1) return launch_glm_fused_r<1>(o, w, g, stream, fx);
+    if (need <= 2) return launch_glm_fused_r<2>(o, w, g, stream, fx);
+    if (need <= 4) return launch_glm_fused_r<4>(o, w, g, stream, fx);
+    if (need <= 8) return launch_glm_fused_r<8>(o, w, g, stream, fx);
+    if (need <= 12) return launch_glm_fused<12, 1>(o, w, g, stream, fx);
+    if (need <= 16) return launch_glm_fused<16, 1>(o, w, g, stream, fx);
+    if (need <= 20) return launch_glm_fused<20, 1>(o, w, g, stream, fx);
     return LBFGSB200_ERR_UNSUPPORTED;
 }
 
