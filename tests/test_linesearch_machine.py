@@ -122,3 +122,61 @@ def test_machine_edge_cases(oracle):
 def test_negative_step_is_find_error():
     pp = R.default_param()
     assert R.lib().lbfgsb200_linesearch_begin(C.byref(pp), 0, 1.0, -1.0, -0.5) is None  # src/line.rs:198-201
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+def test_machine_replays_oracle_on_pathological_values(oracle, algo):
+    """NaN / +-inf objective values and gradients, and an Err from evaluate, at the k-th trial of a search: the
+    machine must take the same branches as the reference's comparisons do (NaN compares false everywhere)."""
+    x0 = np.array([-1.2, 1.0] * 5)
+    g0 = np.zeros(10)
+    rosen(x0, g0)
+    d = -g0
+    L = R.lib()
+    for k_bad in (1, 2, 3):
+        for kind in ("nan_f", "inf_f", "-inf_f", "nan_g", "inf_g", "err"):
+            calls = []
+
+            def fn(x, g, k_bad=k_bad, kind=kind):
+                f = rosen(x, g)
+                if len(calls) == k_bad:          # calls[0] is the evaluation at x0
+                    if kind == "err":
+                        calls.append(None)
+                        return None
+                    if kind == "nan_f":
+                        f = float("nan")
+                    elif kind == "inf_f":
+                        f = float("inf")
+                    elif kind == "-inf_f":
+                        f = float("-inf")
+                    elif kind == "nan_g":
+                        g[:] = float("nan")
+                    elif kind == "inf_g":
+                        g[0] = float("inf")
+                calls.append((f, g.copy()))
+                return f
+            step0 = 1e-3
+            op = oracle.default_param(ls_algorithm=algo)
+            ref = oracle.line_search(op, x0.copy(), d, step0, oracle.Objective.python(fn))
+            assert ref["rc"] == 0
+            f0, g_first = calls[0]
+            dginit = oracle.lib().oracle_vecdot(g_first, np.ascontiguousarray(d), d.size)
+            pp = R.default_param()
+            pp.ls_algorithm = algo
+            h = L.lbfgsb200_linesearch_begin(C.byref(pp), 0, f0, dginit, step0)
+            stp = C.c_double()
+            k = 0
+            while L.lbfgsb200_linesearch_next(h, C.byref(stp)):
+                k += 1
+                assert k < len(calls), (algo, k_bad, kind, "product asked for more trials than the oracle evaluated")
+                if calls[k] is None:
+                    L.lbfgsb200_linesearch_feed(h, 0, 0.0, 0.0)
+                else:
+                    f, g = calls[k]
+                    L.lbfgsb200_linesearch_feed(h, 1, f, oracle.lib().oracle_vecdot(g, np.ascontiguousarray(d), d.size))
+            ncall, step = C.c_int64(), C.c_double()
+            err = L.lbfgsb200_linesearch_result(h, C.byref(ncall), C.byref(step))
+            L.lbfgsb200_linesearch_end(h)
+            assert k == len(calls) - 1, (algo, k_bad, kind)
+            assert (err, ncall.value) == (ref["ls_error"], ref["ncall"]), (algo, k_bad, kind, err, ref)
+            assert step.value == ref["step"] or (np.isnan(step.value) and np.isnan(ref["step"])), (algo, k_bad, kind)
