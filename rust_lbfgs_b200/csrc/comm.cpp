@@ -82,6 +82,7 @@ struct Comm {
     PeerCtx peer{};                    // nranks == 0: not available, use NCCL
     unsigned long long seq = 0;        // exchange counter, advanced identically on every rank
     double *mailbox = nullptr;         // this rank's ring: kMailRing x nranks entries of kMailStride doubles
+    double **mail_table = nullptr;     // device array of every rank's mailbox pointer (as mapped here)
     void *opened[kMaxPeers] = {};
 };
 
@@ -116,15 +117,18 @@ bool setup_peer_mailboxes(Comm *c) {
     bool all_ok = talk;
     for (int r = 0; all_ok && r < c->nranks; ++r) all_ok = host[rec * r + sizeof(mine)] == 1;
     if (all_ok) {
+        double *table[kMaxPeers] = {};
         for (int r = 0; r < c->nranks; ++r) {
-            if (r == c->rank) { c->peer.mail[r] = c->mailbox; continue; }
+            if (r == c->rank) { table[r] = c->mailbox; continue; }
             cudaIpcMemHandle_t h;
             memcpy(&h, &host[rec * r], sizeof(h));
             void *p = nullptr;
             if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; cudaGetLastError(); break; }
             c->opened[r] = p;
-            c->peer.mail[r] = (double *)p;
+            table[r] = (double *)p;
         }
+        if (all_ok) all_ok = cudaMalloc((void **)&c->mail_table, sizeof(table)) == cudaSuccess &&
+                             cudaMemcpy(c->mail_table, table, sizeof(table), cudaMemcpyHostToDevice) == cudaSuccess;
     }
     // second round: did every rank manage to map every peer?
     double *flag = (double *)dev;
@@ -140,11 +144,14 @@ bool setup_peer_mailboxes(Comm *c) {
     if (!all_ok) {
         for (int r = 0; r < kMaxPeers; ++r) if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }
         if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+        if (c->mail_table) { cudaFree(c->mail_table); c->mail_table = nullptr; }
         c->peer = PeerCtx{};
         return false;
     }
     c->peer.nranks = c->nranks;
     c->peer.rank = c->rank;
+    c->peer.mail_self = c->mailbox;
+    c->peer.mail_table = c->mail_table;
     c->peer.seq = 0;
     c->peer.extra[0] = c->peer.extra[1] = nullptr;
     return true;
@@ -228,6 +235,7 @@ void lbfgsb200_comm_destroy(lbfgsb200_comm_t *comm) {
     for (int r = 0; r < lb::kMaxPeers; ++r)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     if (c->mailbox) cudaFree(c->mailbox);
+    if (c->mail_table) cudaFree(c->mail_table);
     if (n.ok && c->comm) n.CommDestroy(c->comm);
     delete c;
 }

@@ -667,12 +667,9 @@ void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n,
 
 __global__ void k_peer_allreduce(PeerCtx pc, double *buf, int count) {
     __shared__ double tab[kMaxPeers + 1][kMailVals];
-    double vals[kMailVals];
-    if (threadIdx.x == 0)
-        for (int a = 0; a < count; ++a) vals[a] = buf[a];
-    peer_allreduce(pc, vals, count, tab);
-    if (threadIdx.x == 0)
-        for (int a = 0; a < count; ++a) buf[a] = vals[a];
+    if (threadIdx.x < count) tab[kMaxPeers][threadIdx.x] = buf[threadIdx.x];
+    peer_allreduce(pc, count, tab);
+    if (threadIdx.x < count) buf[threadIdx.x] = tab[kMaxPeers][threadIdx.x];
 }
 void launch_peer_allreduce(const Launch &L, double *buf, int count) {
     ReduceWs ws = L.ws;

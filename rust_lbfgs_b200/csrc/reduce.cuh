@@ -44,28 +44,29 @@ __device__ __forceinline__ void block_sum(double (&acc)[NACC], double (*sm)[kWar
     }
 }
 
-// Sum `vals[0..nv)` (valid in thread 0 of the calling CTA) over all ranks through the peer mailboxes; every thread
-// of warp 0 must call it, the result is valid in thread 0.  See PeerCtx in types.h.
+// Sum nv values over all ranks through the peer mailboxes; every thread of warp 0 must call it.  See PeerCtx in
+// types.h.
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void peer_allreduce(const PeerCtx &pc, double *vals, int nv, double (*tab)[kMailVals]) {
+// In/out: tab[kMaxPeers][0..nv) in shared memory (written by lane 0 before the call, read by it afterwards).
+__device__ __forceinline__ void peer_allreduce(const PeerCtx &pc, int nv, double (*tab)[kMailVals]) {
     const int lane = threadIdx.x & 31;
     const unsigned long long seq = pc.seq;
     const size_t entry = (size_t)(seq & (kMailRing - 1)) * pc.nranks;
-    if (lane == 0)
-        for (int a = 0; a < nv; ++a) tab[kMaxPeers][a] = vals[a];
+    double *mail_lane = (lane < pc.nranks) ? pc.mail_table[lane] : nullptr;   // the peers' mailboxes, from device memory
+    double *mail_self = pc.mail_self;
     __syncwarp();
     if (lane < pc.nranks) {  // lane t publishes this rank's totals into rank t's mailbox (a peer store over NVLink)
-        volatile double *dst = pc.mail[lane] + (entry + pc.rank) * kMailStride;
+        volatile double *dst = mail_lane + (entry + pc.rank) * kMailStride;
         for (int a = 0; a < nv; ++a) dst[1 + a] = tab[kMaxPeers][a];
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(dst) = seq;
     }
     if (lane < pc.nranks) {  // lane t collects sender t's entry from the local mailbox
-        volatile double *src = pc.mail[pc.rank] + (entry + lane) * kMailStride;
+        volatile double *src = mail_self + (entry + lane) * kMailStride;
         const unsigned long long t0 = globaltimer_ns();
         bool ok = true;
         while (*reinterpret_cast<volatile unsigned long long *>(src) != seq) {
@@ -75,14 +76,12 @@ __device__ __forceinline__ void peer_allreduce(const PeerCtx &pc, double *vals, 
         for (int a = 0; a < nv; ++a) tab[lane][a] = ok ? src[1 + a] : __longlong_as_double(0x7ff8000000000000ll);
     }
     __syncwarp();
-    if (lane < nv) {
-        double v = 0.0;
+    double v = 0.0;
+    if (lane < nv)
         for (int r = 0; r < pc.nranks; ++r) v += tab[r][lane];  // fixed rank order
-        tab[kMaxPeers][lane] = v;
-    }
     __syncwarp();
-    if (lane == 0)
-        for (int a = 0; a < nv; ++a) vals[a] = tab[kMaxPeers][a];
+    if (lane < nv) tab[kMaxPeers][lane] = v;
+    __syncwarp();
 }
 
 // Level 1 + level 2.  `out[a]` receives the grid-wide sum of accumulator a.
@@ -118,22 +117,21 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NACC], const ReduceWs 
     if (ws.peer.nranks > 1) {  // level 3: the same totals from every GPU, summed in rank order (warp 0)
         __shared__ double tab[kMaxPeers + 1][kMailVals];
         if (threadIdx.x < 32) {
-            double vals[NACC + 2];
             int nv = NACC;
             if (threadIdx.x == 0) {
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) vals[a] = acc[a];
-                if (ws.peer.extra[0]) vals[nv++] = *ws.peer.extra[0];
-                if (ws.peer.extra[1]) vals[nv++] = *ws.peer.extra[1];
+                for (int a = 0; a < NACC; ++a) tab[kMaxPeers][a] = acc[a];
+                if (ws.peer.extra[0]) tab[kMaxPeers][nv++] = *ws.peer.extra[0];
+                if (ws.peer.extra[1]) tab[kMaxPeers][nv++] = *ws.peer.extra[1];
             }
             nv = __shfl_sync(0xffffffffu, nv, 0);
-            peer_allreduce(ws.peer, vals, nv, tab);
+            peer_allreduce(ws.peer, nv, tab);
             if (threadIdx.x == 0) {
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) acc[a] = vals[a];
+                for (int a = 0; a < NACC; ++a) acc[a] = tab[kMaxPeers][a];
                 int k = NACC;
-                if (ws.peer.extra[0]) *ws.peer.extra[0] = vals[k++];
-                if (ws.peer.extra[1]) *ws.peer.extra[1] = vals[k++];
+                if (ws.peer.extra[0]) *ws.peer.extra[0] = tab[kMaxPeers][k++];
+                if (ws.peer.extra[1]) *ws.peer.extra[1] = tab[kMaxPeers][k++];
             }
         }
     }

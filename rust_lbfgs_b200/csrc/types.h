@@ -47,7 +47,8 @@ struct PeerCtx {
     int nranks;                    // 0 / 1 = no exchange
     int rank;
     unsigned long long seq;        // this launch's sequence number (same on every rank)
-    double *mail[kMaxPeers];       // mail[r]: rank r's mailbox as mapped into this process (mail[rank] is local)
+    double *mail_self;             // this rank's mailbox
+    double *const *mail_table;     // device array: mail_table[r] = rank r's mailbox as mapped into this process
     double *extra[2];              // optional device scalars that ride along with the exchange (summed in place)
 };
 
