@@ -116,8 +116,8 @@ def algorithmic_bytes_survey(n, launches, kbytes):
     V = 8n bytes: trial step 3V t + post-eval dots 3V t + history update 7V + two-loop (8b - 1) V.
     t and b are the MEASURED evaluation / two-loop trip counts of the timed region."""
     V = 8.0 * n
-    t = launches["evaluate"] + launches.get("trial_eval", 0)
-    iters = launches["history"]
+    t = launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)
+    iters = launches["history"] + launches.get("commit", 0)
     return 8.0 * t * V + 7.0 * iters * V + kbytes["backward"] + kbytes["forward"]
 
 
@@ -318,8 +318,9 @@ def run_ours(args):
         # SURVEY.md §8(d)'s formula prices a trial at 8V (K1 + evaluate + K2); the fused trial moves 4V, so this
         # "unfused-equivalent" rate can exceed what the HBM actually carried — reported for comparison only
         "survey_formula_equivalent_GBps": surv_bytes / 1e9 / (ms_total / 1e3),
-        "fused_trial": bool(launches.get("trial_eval", 0) > 0),
-        "evaluations_per_iteration": (launches["evaluate"] + launches.get("trial_eval", 0)) / max(1, K),
+        "line_search_trials": ("probe + commit" if launches.get("probe", 0) > 0 else
+                               "fused trial" if launches.get("trial_eval", 0) > 0 else "unfused (K1 + evaluate + K2)"),
+        "evaluations_per_iteration": (launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)) / max(1, K),
         "kernel_ms_timed_region": {k: round(v, 3) for k, v in kms.items() if v > 0},
         "profile_pass": {
             "note": f"{P} extra iterations after the timed region with CUDA events around every launch",

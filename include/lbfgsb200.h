@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LBFGSB200_ABI_VERSION 2
+#define LBFGSB200_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -136,6 +136,37 @@ typedef int (*lbfgsb200_trial_eval_fn)(void *user, const double *xp_dev, const d
                                        double *x_dev, double *g_dev, int64_t n_local, void *stream,
                                        double *out_dev);
 
+/* PROBE + COMMIT: the fused line search without wasted writes.  A line search evaluates t trial points and
+ * keeps one; only {f, g.d} of the rejected ones are ever used (src/line.rs:283-320, :741-760).  So a trial is a
+ * PROBE that reads xp and d and writes nothing (2R instead of the fused trial's 2R 2W):
+ *   out_dev[0..3] = partial f(xp + step*d), g.d, g.g, x.x          (same sums as lbfgsb200_trial_eval_fn)
+ * and, once the search has accepted a step, ONE COMMIT pass materialises the point and performs
+ * IterationData::update's vector work (src/lbfgs.rs:640-656, :670-673) on the way:
+ *   x = xp + step*d;  g = grad f(x);  s = x - xp;  y = g - gp
+ *   out_dev[0..4] = partial s.s, y.s, y.y, s.(-g), s.(gp*bs_scale)      (bs_scale = -step_returned, for damping)
+ * 3R 4W; per iteration 2t + 7 passes replace the fused trial's 4t + 6.  Element-wise arithmetic must be that of
+ * the unfused kernels (no FMA), so that all three paths produce the same bits.  Same rules as lbfgsb200_eval_fn:
+ * enqueue on `stream`, do not synchronise, non-zero = Err.  Not used for OWL-QN. */
+typedef int (*lbfgsb200_probe_fn)(void *user, const double *xp_dev, const double *d_dev, double step,
+                                  int64_t n_local, void *stream, double *out_dev);
+typedef int (*lbfgsb200_commit_fn)(void *user, const double *xp_dev, const double *d_dev, const double *gp_dev,
+                                   double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
+                                   double *y_dev, int64_t n_local, void *stream, double *out_dev);
+
+/* What an objective offers beyond lbfgsb200_eval_fn.  Unused entries are NULL.  probe needs commit. */
+#define LBFGSB200_FUSED_SUMS_OVER_RANKS 1  /* the callbacks leave sums over ALL ranks in out_dev (the built-in
+                                              objectives do, in their kernels' epilogue, once
+                                              lbfgsb200_objective_set_shard gave them the communicator); such a
+                                              callback must fail on every rank or on none */
+typedef struct lbfgsb200_fused_ops {
+    int64_t struct_size;                /* sizeof(lbfgsb200_fused_ops_t) */
+    lbfgsb200_trial_eval_fn trial;      /* one-pass trial that writes x and g */
+    lbfgsb200_probe_fn probe;           /* write-free trial */
+    lbfgsb200_commit_fn commit;         /* accepted point + history update */
+    void *user;
+    int64_t flags;                      /* LBFGSB200_FUSED_* */
+} lbfgsb200_fused_ops_t;
+
 /* Progress  src/core.rs:221-250; x/gx are device pointers to this rank's shard */
 typedef struct lbfgsb200_progress {
     const double *x_dev;
@@ -201,6 +232,10 @@ int lbfgsb200_minimize(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval
 
 /* Registers (fn != NULL) or clears the fused trial evaluate for the following build()/minimize() calls. */
 int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eval_fn fn, void *user);
+/* Registers everything an objective offers (ops != NULL) or clears it (NULL) for the following build()/minimize()
+ * calls.  With probe + commit the line search runs write-free probes and one commit per iteration; with only
+ * `trial` it runs the one-pass trial; otherwise K1 + evaluate + K2.  All three give the same bits. */
+int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_ops_t *ops);
 
 /* The iterative API  src/lbfgs.rs:443-566 */
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user);
@@ -222,11 +257,12 @@ int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int6
                             lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
                             void *progress_user, lbfgsb200_report_t *report);
 
-/* The same with everything the device API offers: this rank's shard of a sharded vector (comm != NULL) and an
- * optional fused trial evaluate.  x_host should be pinned memory for full PCIe speed. */
+/* The same with everything the device API offers: this rank's shard of a sharded vector (comm != NULL) and the
+ * objective's fused line-search entries (fused may be NULL).  x_host should be pinned memory for full PCIe
+ * speed. */
 int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, int64_t n_local, int64_t n_global,
                                int64_t global_offset, int device, lbfgsb200_comm_t *comm, lbfgsb200_eval_fn eval,
-                               void *eval_user, lbfgsb200_trial_eval_fn trial_eval, void *trial_user,
+                               void *eval_user, const lbfgsb200_fused_ops_t *fused,
                                lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
@@ -243,7 +279,10 @@ enum {
     LBFGSB200_K_EVALUATE = 9,   /* the user's device evaluate */
     LBFGSB200_K_PRIMITIVE = 10, /* unfused LbfgsMath primitives                      src/math.rs:31-82 */
     LBFGSB200_K_TRIAL_EVAL = 11,/* fused trial step + evaluate + dots (lbfgsb200_trial_eval_fn) */
-    LBFGSB200_K_COUNT = 12
+    LBFGSB200_K_PROBE = 12,     /* write-free trial (lbfgsb200_probe_fn) */
+    LBFGSB200_K_COMMIT = 13,    /* accepted point + history update (lbfgsb200_commit_fn) */
+    LBFGSB200_K_UPDATE_SMALL = 14, /* launch-bound regime: history + whole two-loop in ONE cooperative kernel */
+    LBFGSB200_K_COUNT = 15
 };
 typedef struct lbfgsb200_profile {
     int64_t launches[LBFGSB200_K_COUNT];        /* kernels launched (evaluate: callback invocations) */
@@ -285,6 +324,36 @@ int lbfgsb200_owl_orthant(signed char *wp_dev, const double *xp_dev, const doubl
 int lbfgsb200_owl_constrain_direction(double *d_dev, const double *pg_dev, int64_t n, int64_t start,
                                       int64_t end, void *stream, double out_host[1]);
 
+/* The update chain's own kernels, one call each.  Scalars that the solver keeps on the device (alpha, beta,
+ * y.s, gamma) are passed BY VALUE here and uploaded by the wrapper, so every production kernel can be driven
+ * with arbitrary vectors.  Results are read back with one stream synchronisation per call. */
+/* d = -g; out = {d.d, g.d}                                             src/core.rs:95-101, src/lbfgs.rs:457-461 */
+int lbfgsb200_init_direction(double *d_dev, const double *g_dev, int64_t n, void *stream, double out_host[2]);
+/* IterationData::update's vector work (src/lbfgs.rs:640-656, :670-673): s = x - xp, y = g - gp,
+ *   out = {s.s, y.s, y.y, s.(-g), s.(gp * -step)}   (the last one only with damping != 0, else 0)
+ * pg_dev non-NULL (OWL-QN): out[3] = s.(-pg), the first alpha's numerator with d = -pg (src/core.rs:96-97) */
+int lbfgsb200_history_update(double *s_dev, double *y_dev, const double *x_dev, const double *xp_dev,
+                             const double *g_dev, const double *gp_dev, const double *pg_dev, int64_t n,
+                             double step, int damping, void *stream, double out_host[5]);
+/* Powell damping (src/lbfgs.rs:664-689), decided by the kernel from y.s and s.Bs: case 1 (y.s < 0.4 s.Bs)
+ * rewrites y = ((gp * -step) * (1 - theta)) + theta * y, theta = 0.6 s.Bs / (s.Bs - y.s); otherwise y is left
+ * alone (case 2 computes and discards).  *applied_host = 1 when y was rewritten. */
+int lbfgsb200_damp_y(double *y_dev, const double *gp_dev, int64_t n, double step, double ys, double sbs,
+                     void *stream, int *applied_host);
+/* One trip of the backward loop (src/lbfgs.rs:582-591): alpha = sq / ys_j; q = q - alpha*y_j, where the first
+ * trip takes q = -g from g_first_dev (non-NULL) instead of reading q.  s_next_dev non-NULL: out = {alpha,
+ * s_next.q} (the next trip's numerator); NULL (last trip): q *= gamma (:591) and out = {alpha, y_j.q} */
+int lbfgsb200_two_loop_backward_step(double *q_dev, const double *g_first_dev, const double *y_j_dev,
+                                     const double *s_next_dev, int64_t n, double sq, double ys_j, double gamma,
+                                     void *stream, double out_host[2]);
+/* One trip of the forward loop (src/lbfgs.rs:594-601): beta = yr / ys_j; r += (alpha_j - beta)*s_j.
+ * y_next_dev non-NULL: out = {beta, y_next.r}.  NULL (last trip): g_last_dev = g, out = {beta, r.r, g.r}
+ * (src/lbfgs.rs:543, src/core.rs:78-92); with owl != 0 g_last_dev = pg and the direction is projected on
+ * [owl_start, owl_end) (src/orthantwise.rs:140-161): out = {beta, r.r before, pg.d after, d.d after} */
+int lbfgsb200_two_loop_forward_step(double *r_dev, const double *s_j_dev, const double *y_next_dev,
+                                    const double *g_last_dev, int64_t n, double yr, double ys_j, double alpha_j,
+                                    int owl, int64_t owl_start, int64_t owl_end, void *stream, double out_host[4]);
+
 /* ---- built-in device objectives (lbfgsb200_eval_fn-compatible) ------------------------------ */
 typedef struct lbfgsb200_objective lbfgsb200_objective_t;
 /* default_evaluate (Rosenbrock)  src/lib.rs:79-94; n_local must be even */
@@ -301,7 +370,9 @@ void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective);
 /* LBFGSB200_REDUCE_* for the objective's own sum (f); SEQUENTIAL is implemented for Rosenbrock, Booth and
  * Lennard-Jones (exp/log in the GLMs are not bit-reproducible against a CPU libm anyway) */
 int  lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int reduction);
-/* Multi-GPU objectives.  Rosenbrock is shard-local (no-op).
+/* Multi-GPU objectives.  Rosenbrock is shard-local: nothing to exchange for evaluate; its fused
+ * trial / probe / commit kernels use the communicator to sum their scalars over the ranks in their own epilogue
+ * (LBFGSB200_FUSED_SUMS_OVER_RANKS), so a trial costs no extra launch on N GPUs.
  *   GLM: this rank's X / y hold a block of ROWS; w is replicated on every rank and the solver runs unsharded
  *        (comm = NULL in lbfgsb200_create): eval all-reduces f and the ncol-vector gradient, so every rank sees the
  *        same bits.  shard_offsets is ignored.
@@ -319,6 +390,16 @@ int  lbfgsb200_objective_eval(void *objective, const double *x_dev, double *g_de
 int  lbfgsb200_objective_trial_eval(void *objective, const double *xp_dev, const double *d_dev, double step,
                                     double *x_dev, double *g_dev, int64_t n_local, void *stream, double *out_dev);
 int  lbfgsb200_objective_has_trial_eval(const lbfgsb200_objective_t *objective);
+/* the lbfgsb200_probe_fn / lbfgsb200_commit_fn of the built-in objectives (Rosenbrock; the others return
+ * LBFGSB200_ERR_UNSUPPORTED), and everything an objective offers in one struct (entries it lacks are NULL;
+ * flags has LBFGSB200_FUSED_SUMS_OVER_RANKS once lbfgsb200_objective_set_shard attached a communicator whose
+ * peer mailboxes the kernels can use). */
+int  lbfgsb200_objective_probe(void *objective, const double *xp_dev, const double *d_dev, double step,
+                               int64_t n_local, void *stream, double *out_dev);
+int  lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
+                                double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
+                                double *y_dev, int64_t n_local, void *stream, double *out_dev);
+int  lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fused_ops_t *out);
 
 /* ---- line-search state machines (pure host code; exposed so the scalar logic can be checked
  *      without a GPU)  src/line.rs:226-399, 446-709, 716-784 ----------------------------------- */

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lbfgsb200.h")
 
 K_NAMES = ["dots", "owl_pg", "init_dir", "trial", "orthant", "history", "damp", "backward", "forward",
-           "evaluate", "primitive", "trial_eval"]
+           "evaluate", "primitive", "trial_eval", "probe", "commit", "update_small"]
 K_COUNT = len(K_NAMES)
 
 STATUS_NAMES = {
@@ -24,7 +24,8 @@ STATUS_NAMES = {
     -20: "ERR_CUDA", -21: "ERR_NCCL", -22: "ERR_STATE", -23: "ERR_UNSUPPORTED",
 }
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+FUSED_SUMS_OVER_RANKS = 1
 LS_MORETHUENTE, LS_BACKTRACKING_ARMIJO, LS_BACKTRACKING_WOLFE, LS_BACKTRACKING_STRONG_WOLFE = 0, 1, 2, 3
 UNIQUE_ID_BYTES = 128
 
@@ -68,6 +69,15 @@ EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.
 TRIAL_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
                             C.c_void_p, C.c_void_p)
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Progress))
+PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p)
+COMMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
+class FusedOps(C.Structure):
+    """lbfgsb200_fused_ops_t: what an objective offers beyond evaluate (function pointers as void*)."""
+    _fields_ = [("struct_size", C.c_int64), ("trial", C.c_void_p), ("probe", C.c_void_p), ("commit", C.c_void_p),
+                ("user", C.c_void_p), ("flags", C.c_int64)]
 
 _lib = None
 
@@ -123,7 +133,16 @@ def lib():
     _sig(L, "lbfgsb200_gx", vp, [vp])
     _sig(L, "lbfgsb200_direction", vp, [vp])
     _sig(L, "lbfgsb200_minimize_host", i32, [pp(Param), vp, i64, i32, vp, vp, vp, vp, pp(Report)])
-    _sig(L, "lbfgsb200_minimize_host_ex", i32, [pp(Param), vp, i64, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, pp(Report)])
+    _sig(L, "lbfgsb200_minimize_host_ex", i32, [pp(Param), vp, i64, i64, i64, i32, vp, vp, vp, pp(FusedOps), vp, vp, pp(Report)])
+    _sig(L, "lbfgsb200_set_fused_ops", i32, [vp, pp(FusedOps)])
+    _sig(L, "lbfgsb200_init_direction", i32, [vp, vp, i64, vp, pp(dbl)])
+    _sig(L, "lbfgsb200_history_update", i32, [vp, vp, vp, vp, vp, vp, vp, i64, dbl, i32, vp, pp(dbl)])
+    _sig(L, "lbfgsb200_damp_y", i32, [vp, vp, i64, dbl, dbl, dbl, vp, pp(i32)])
+    _sig(L, "lbfgsb200_two_loop_backward_step", i32, [vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, pp(dbl)])
+    _sig(L, "lbfgsb200_two_loop_forward_step", i32, [vp, vp, vp, vp, i64, dbl, dbl, dbl, i32, i64, i64, vp, pp(dbl)])
+    _sig(L, "lbfgsb200_objective_probe", i32, [vp, vp, vp, dbl, i64, vp, vp])
+    _sig(L, "lbfgsb200_objective_commit", i32, [vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, i64, vp, vp])
+    _sig(L, "lbfgsb200_objective_fused_ops", i32, [vp, pp(FusedOps)])
     _sig(L, "lbfgsb200_profile_enable", i32, [vp, i32])
     _sig(L, "lbfgsb200_profile_get", i32, [vp, pp(Profile)])
     _sig(L, "lbfgsb200_profile_reset", i32, [vp])

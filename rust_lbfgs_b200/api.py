@@ -96,15 +96,17 @@ def _current_stream(device):
 class _Evaluate:
     """Adapts a built-in objective or a Python callable to lbfgsb200_eval_fn."""
 
-    def __init__(self, evaluate, device, reduction=0, fused=True):
+    def __init__(self, evaluate, device, reduction=0, fused=True, comm=None):
         self.keep = []
-        self.trial_fn = None
+        self.fused_ops = None        # _lib.FusedOps or None
         if hasattr(evaluate, "_eval_ptr"):
+            if comm is not None and evaluate._auto_shard and evaluate._shard is None:
+                evaluate.shard(comm)
             self.fn = evaluate._eval_ptr()
             self.user = evaluate._user_ptr(device)
             evaluate._set_reduction(device, reduction)
             if fused:
-                self.trial_fn = evaluate._trial_eval_ptr(device)
+                self.fused_ops = evaluate._fused_ops(device, fused)
             self.keep.append(evaluate)
         elif callable(evaluate):
             import torch
@@ -269,9 +271,14 @@ class Lbfgs:
         return self
 
     def with_fused_trial(self, fused):
-        """Use the objective's fused line-search trial (x = xp + step*d, evaluate and the three dots in one
-        pass) when it has one; default True.  Results are bit-identical either way."""
-        self._fused_trial = bool(fused)
+        """How line-search trials run when the objective offers fused entries (lbfgsb200_fused_ops_t):
+        True / "probe" (default): write-free probes (read xp and d, emit f, g.d, g.g, x.x) and ONE commit per
+        iteration that materialises the accepted x and g and forms s, y and the history sums in the same pass;
+        "trial": the one-pass trial that writes x and g every time; False: K1 + evaluate + K2 (three passes).
+        Results are bit-identical in all three modes."""
+        if fused not in (True, False, "probe", "trial"):
+            raise ValueError("fused must be True, False, 'probe' or 'trial'")
+        self._fused_trial = fused
         return self
 
     def with_shard(self, comm, n_global, global_offset):
@@ -290,8 +297,8 @@ class Lbfgs:
         ptr, n, device = _ptr_n_device(x)
         solver = _make_solver(self, n, device)
         try:
-            ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial)
-            L.lbfgsb200_set_trial_evaluate(solver, ev.trial_fn, ev.user if ev.trial_fn else None)
+            ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial, self._comm)
+            _set_fused(L, solver, ev)
             cb = None
             cbp = None
             if progress is not None:
@@ -326,7 +333,7 @@ class Lbfgs:
             ptr, n = int(x_host.ctypes.data), int(x_host.size)
         n_global, goff = (n, 0) if self._shard is None else self._shard
         comm = self._comm._handle if self._comm is not None else None
-        ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial)
+        ev = _Evaluate(evaluate, device, self.param.reduction, self._fused_trial, self._comm)
         cb = cbp = None
         if progress is not None:
             def on_progress(_user, pp):
@@ -335,7 +342,8 @@ class Lbfgs:
             cbp = C.cast(cb, C.c_void_p)
         rep = _lib.Report()
         st = L.lbfgsb200_minimize_host_ex(C.byref(self.param), ptr, n, n_global, goff, device, comm, ev.fn, ev.user,
-                                          ev.trial_fn, ev.user if ev.trial_fn else None, cbp, None, C.byref(rep))
+                                          C.byref(ev.fused_ops) if ev.fused_ops is not None else None, cbp, None,
+                                          C.byref(rep))
         report = _report_from_c(rep)
         report.status = st
         if st == -5:
@@ -359,8 +367,8 @@ class LbfgsState:
         self._device = device
         self._x_owner = x
         self._solver = _make_solver(builder, n, device)
-        self._ev = _Evaluate(evaluate, device, builder.param.reduction, builder._fused_trial)
-        self._L.lbfgsb200_set_trial_evaluate(self._solver, self._ev.trial_fn, self._ev.user if self._ev.trial_fn else None)
+        self._ev = _Evaluate(evaluate, device, builder.param.reduction, builder._fused_trial, builder._comm)
+        _set_fused(self._L, self._solver, self._ev)
         st = self._L.lbfgsb200_build(self._solver, ptr, self._ev.fn, self._ev.user)
         if st != 0:
             msg = self._L.lbfgsb200_last_error(self._solver).decode()
@@ -429,6 +437,12 @@ class LbfgsState:
 
 
 # ---- helpers --------------------------------------------------------------------------------------
+def _set_fused(L, solver, ev):
+    st = L.lbfgsb200_set_fused_ops(solver, C.byref(ev.fused_ops) if ev.fused_ops is not None else None)
+    if st != 0:
+        raise LbfgsError(st, "lbfgsb200_set_fused_ops failed")
+
+
 def _require(cond, msg):
     if not cond:
         raise ValueError(msg)  # the reference's assert!(.., msg) panics

@@ -26,9 +26,11 @@ inline const Solver *S(const lbfgsb200_solver_t *s) { return reinterpret_cast<co
 struct PrimCtx {
     lb::DeviceInfo dev{};
     lb::ReduceWs ws{};
-    double *out_dev = nullptr;
+    double *out_dev = nullptr;      // kMaxAcc result doubles, then kPrimIn uploaded scalars (the exported fused steps)
+    std::mutex mu;                  // one launch + read-back at a time per device: ticket, partials and out_dev are shared
     bool ok = false;
 };
+constexpr int kPrimIn = 16;
 std::mutex g_prim_mu;
 std::map<int, PrimCtx> g_prim;
 
@@ -42,7 +44,7 @@ int prim_ctx(PrimCtx **out) {
         if (rc != 0) return rc;
         rc = lb::alloc_reduce_ws(c.dev, &c.ws);
         if (rc != 0) return rc;
-        if (cudaMalloc((void **)&c.out_dev, sizeof(double) * lb::kMaxAcc) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+        if (cudaMalloc((void **)&c.out_dev, sizeof(double) * (lb::kMaxAcc + kPrimIn)) != cudaSuccess) return LBFGSB200_ERR_CUDA;
         c.ok = true;
     }
     *out = &c;
@@ -130,6 +132,13 @@ int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eva
     S(solver)->set_trial_evaluate(fn, user);
     return 0;
 }
+int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_ops_t *ops) {
+    if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
+    if (ops && (ops->struct_size != (int64_t)sizeof(lbfgsb200_fused_ops_t) || (ops->probe && !ops->commit)))
+        return LBFGSB200_ERR_INVALID_PARAM;
+    S(solver)->set_fused_ops(ops);
+    return 0;
+}
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
     return S(solver)->build(x_dev, eval, eval_user);
@@ -157,7 +166,7 @@ const double *lbfgsb200_direction(const lbfgsb200_solver_t *solver) { return sol
 
 int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, int64_t n_local, int64_t n_global,
                                int64_t global_offset, int device, lbfgsb200_comm_t *comm, lbfgsb200_eval_fn eval,
-                               void *eval_user, lbfgsb200_trial_eval_fn trial_eval, void *trial_user,
+                               void *eval_user, const lbfgsb200_fused_ops_t *fused,
                                lbfgsb200_progress_fn progress, void *progress_user, lbfgsb200_report_t *report) {
     if (!param || !x_host || n_local < 1 || !eval) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
@@ -186,7 +195,7 @@ int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, i
         x_dev = S(solver)->spare_x();   // the device copy of x lives in the solver's (pooled) arena
         if (cudaMemcpyAsync(x_dev, x_host, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) break;
         lap("H2D enqueue");
-        if (trial_eval) lbfgsb200_set_trial_evaluate(solver, trial_eval, trial_user);
+        if (fused && (status = lbfgsb200_set_fused_ops(solver, fused)) != 0) break;
         status = lbfgsb200_minimize(solver, x_dev, eval, eval_user, progress, progress_user, report);
         lap("minimize");
         if (cudaMemcpyAsync(x_host, x_dev, bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
@@ -207,7 +216,7 @@ int lbfgsb200_minimize_host_ex(const lbfgsb200_param_t *param, double *x_host, i
 int lbfgsb200_minimize_host(const lbfgsb200_param_t *param, double *x_host, int64_t n, int device,
                             lbfgsb200_eval_fn eval, void *eval_user, lbfgsb200_progress_fn progress,
                             void *progress_user, lbfgsb200_report_t *report) {
-    return lbfgsb200_minimize_host_ex(param, x_host, n, n, 0, device, nullptr, eval, eval_user, nullptr, nullptr, progress,
+    return lbfgsb200_minimize_host_ex(param, x_host, n, n, 0, device, nullptr, eval, eval_user, nullptr, progress,
                                       progress_user, report);
 }
 
@@ -233,6 +242,7 @@ int lbfgsb200_profile_reset(lbfgsb200_solver_t *solver) {
     PrimCtx *c = nullptr;                                            \
     int rc = prim_ctx(&c);                                           \
     if (rc != 0) return rc;                                          \
+    std::lock_guard<std::mutex> prim_lock(c->mu);                    \
     lb::Launch L = prim_launch(*c, stream, n, NVEC);
 
 int lbfgsb200_vecadd(double *y, const double *x, double cc, int64_t n, void *stream) {
@@ -325,6 +335,78 @@ int lbfgsb200_owl_constrain_direction(double *d, const double *pg, int64_t n, in
     if (!(start < end)) return LBFGSB200_ERR_INVALID_PARAM;
     lb::launch_owl_constrain(L, d, pg, n, start, end, 0, c->out_dev);
     return read_back(*c, stream, 1, out_host);
+}
+
+// ---- the update chain's kernels, one call each ------------------------------------------------------
+namespace {
+// uploads `count` scalars behind the result slot; returns their device address
+const double *upload(PrimCtx *c, void *stream, const double *vals, int count) {
+    double *dst = c->out_dev + lb::kMaxAcc;
+    if (cudaMemcpyAsync(dst, vals, sizeof(double) * count, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return nullptr;
+    return dst;   // `vals` is pageable host memory: the copy has been staged when cudaMemcpyAsync returns
+}
+}  // namespace
+
+int lbfgsb200_init_direction(double *d, const double *g, int64_t n, void *stream, double out_host[2]) {
+    if (!aligned16(d) || !aligned16(g) || !out_host) return LBFGSB200_ERR_INVALID_PARAM;
+    LB_PRIM_PROLOGUE(2)
+    lb::launch_init_dir(L, d, g, n, c->out_dev);
+    return read_back(*c, stream, 2, out_host);
+}
+int lbfgsb200_history_update(double *s, double *y, const double *x, const double *xp, const double *g, const double *gp,
+                             const double *pg, int64_t n, double step, int damping, void *stream, double out_host[5]) {
+    if (!aligned16(s) || !aligned16(y) || !aligned16(x) || !aligned16(xp) || !aligned16(g) || !aligned16(gp) ||
+        (pg && !aligned16(pg)) || !out_host)
+        return LBFGSB200_ERR_INVALID_PARAM;
+    LB_PRIM_PROLOGUE(6)
+    if (cudaMemsetAsync(c->out_dev, 0, sizeof(double) * 5, (cudaStream_t)stream) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    lb::launch_history(L, x, xp, g, gp, pg, s, y, n, -step, damping != 0, c->out_dev);
+    rc = read_back(*c, stream, 5, out_host);
+    if (rc == 0 && !damping) out_host[4] = 0.0;
+    return rc;
+}
+int lbfgsb200_damp_y(double *y, const double *gp, int64_t n, double step, double ys, double sbs, void *stream,
+                     int *applied_host) {
+    if (!aligned16(y) || !aligned16(gp)) return LBFGSB200_ERR_INVALID_PARAM;
+    LB_PRIM_PROLOGUE(2)
+    const double hist[5] = {0.0, ys, 0.0, 0.0, sbs};
+    const double *hist_dev = upload(c, stream, hist, 5);
+    if (!hist_dev) return LBFGSB200_ERR_CUDA;
+    lb::launch_damp(L, y, gp, n, -step, hist_dev);
+    if (applied_host) *applied_host = (ys < (1.0 - 0.6) * sbs) ? 1 : 0;   // the kernel's own test, src/lbfgs.rs:664-675
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+int lbfgsb200_two_loop_backward_step(double *q, const double *g_first, const double *y_j, const double *s_next, int64_t n,
+                                     double sq, double ys_j, double gamma, void *stream, double out_host[2]) {
+    if (!aligned16(q) || !aligned16(y_j) || (g_first && !aligned16(g_first)) || (s_next && !aligned16(s_next)) || !out_host)
+        return LBFGSB200_ERR_INVALID_PARAM;
+    LB_PRIM_PROLOGUE(4)
+    // in: [0] = s_j.q, [1] = y_j.s_j, hist = in + 2: hist[1] / hist[2] = gamma / 1; out: [0] = alpha, [1] = the dot
+    const double in[5] = {sq, ys_j, 0.0, gamma, 1.0};
+    const double *in_dev = upload(c, stream, in, 5);
+    if (!in_dev) return LBFGSB200_ERR_CUDA;
+    lb::launch_backward(L, g_first != nullptr, s_next == nullptr, q, g_first, y_j, s_next, n, in_dev + 0, in_dev + 1, nullptr,
+                        in_dev + 2, c->out_dev + 0, c->out_dev + 1);
+    return read_back(*c, stream, 2, out_host);
+}
+int lbfgsb200_two_loop_forward_step(double *r, const double *s_j, const double *y_next, const double *g_last, int64_t n,
+                                    double yr, double ys_j, double alpha_j, int owl, int64_t owl_start, int64_t owl_end,
+                                    void *stream, double out_host[4]) {
+    const bool last = y_next == nullptr;
+    if (!aligned16(r) || !aligned16(s_j) || (y_next && !aligned16(y_next)) || (last && (!g_last || !aligned16(g_last))) || !out_host)
+        return LBFGSB200_ERR_INVALID_PARAM;
+    LB_PRIM_PROLOGUE(4)
+    if (owl_end < 0 || owl_end > n) owl_end = n;
+    const double in[3] = {yr, ys_j, alpha_j};
+    const double *in_dev = upload(c, stream, in, 3);
+    if (!in_dev) return LBFGSB200_ERR_CUDA;
+    if (cudaMemsetAsync(c->out_dev, 0, sizeof(double) * 4, (cudaStream_t)stream) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    lb::launch_forward(L, last, last && owl != 0, r, s_j, y_next, g_last, n, in_dev + 0, in_dev + 1, in_dev + 2, owl_start,
+                       owl_end, 0, c->out_dev + 1);
+    rc = read_back(*c, stream, 4, out_host);
+    if (rc == 0) out_host[0] = yr / ys_j;   // beta, the kernel's own quotient (src/lbfgs.rs:597)
+    return rc;
 }
 
 // ---- line-search state machine ------------------------------------------------------------------

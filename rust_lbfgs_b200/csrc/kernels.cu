@@ -237,13 +237,7 @@ struct HistoryOp {
     }
     __device__ __forceinline__ void elem(double xi, double xpi, double gi, double gpi, double pgi, double &si,
                                          double &yi, double (&acc)[5]) const {
-        si = xi - xpi;                                      // lbfgs.rs:644
-        yi = gi - gpi;                                      // :647 (raw gradients, also for OWL-QN: :529-530)
-        acc[0] += si * si;                                  // :645
-        acc[1] += yi * si;                                  // :653
-        acc[2] += yi * yi;                                  // :654
-        acc[3] += si * (-(OWL ? pgi : gi));                 // first trip of :587 with d = -g | -pg (core.rs:95-101)
-        if (DAMP) acc[4] += si * (gpi * nstep);             // :670-673, nstep = -step
+        history_elem<DAMP, OWL>(xi, xpi, gi, gpi, pgi, nstep, si, yi, acc);
     }
     __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[5]) const {
         double2 so, yo;

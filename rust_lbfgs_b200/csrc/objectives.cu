@@ -46,6 +46,30 @@ struct Objective {
 };
 
 // ---- Rosenbrock ------------------------------------------------------------------------------
+// One (x0, x1) pair of default_evaluate: the gradient pair and the pair's term of f.  Every Rosenbrock kernel below
+// goes through this one function, so evaluate, the fused trial, the probe and the commit see the same arithmetic.
+__device__ __forceinline__ double rosen_pair(double x0, double x1, double2 &o) {
+    const double t1 = 1.0 - x0;                             // lib.rs:85
+    const double t2 = 10.0 * (x1 - x0 * x0);                // :86
+    o.y = 20.0 * t2;                                        // :87
+    o.x = -2.0 * (x0 * o.y + t1);                           // :88
+    return t1 * t1 + t2 * t2;                               // :89
+}
+// x = xp + step*d for one pair (veccpy + vecadd, core.rs:156-157), then rosen_pair and the trial's four sums
+// {f, g.d, g.g, x.x} (core.rs:114-116,183-194) in the order the unfused kernels add them.
+__device__ __forceinline__ void rosen_trial_pair(double2 xp, double2 d, double step, double2 &xo, double2 &o,
+                                                 double (&acc)[4]) {
+    xo.x = xp.x + step * d.x;
+    xo.y = xp.y + step * d.y;
+    acc[0] += rosen_pair(xo.x, xo.y, o);
+    acc[1] += o.x * d.x;
+    acc[2] += o.x * o.x;
+    acc[3] += xo.x * xo.x;
+    acc[1] += o.y * d.y;
+    acc[2] += o.y * o.y;
+    acc[3] += xo.y * xo.y;
+}
+
 template <bool S>
 struct RosenOp {
     const double *x;
@@ -53,13 +77,8 @@ struct RosenOp {
     struct Regs { double2 x; };
     __device__ __forceinline__ void load(Regs &r, int64_t i) const { r.x = ld2<S>(x, i); }
     __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[1]) const {
-        const double x0 = r.x.x, x1 = r.x.y;
-        const double t1 = 1.0 - x0;                         // lib.rs:85
-        const double t2 = 10.0 * (x1 - x0 * x0);            // :86
         double2 o;
-        o.y = 20.0 * t2;                                    // :87
-        o.x = -2.0 * (x0 * o.y + t1);                       // :88
-        acc[0] += t1 * t1 + t2 * t2;                        // :89
+        acc[0] += rosen_pair(r.x.x, r.x.y, o);
         st2<S>(g, i, o);
     }
     __device__ __forceinline__ void tail(int64_t, double (&)[1]) const {}
@@ -86,22 +105,8 @@ struct RosenTrialOp {
         r.d = ld2<S>(d, i);
     }
     __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[4]) const {
-        double2 xo;
-        xo.x = r.xp.x + step * r.d.x;                       // veccpy + vecadd, core.rs:156-157
-        xo.y = r.xp.y + step * r.d.y;
-        const double x0 = xo.x, x1 = xo.y;
-        const double t1 = 1.0 - x0;                         // lib.rs:85
-        const double t2 = 10.0 * (x1 - x0 * x0);            // :86
-        double2 o;
-        o.y = 20.0 * t2;                                    // :87
-        o.x = -2.0 * (x0 * o.y + t1);                       // :88
-        acc[0] += t1 * t1 + t2 * t2;                        // :89
-        acc[1] += o.x * r.d.x;                              // g.d, core.rs:114-116
-        acc[2] += o.x * o.x;                                // g.g, core.rs:183-190
-        acc[3] += x0 * x0;                                  // x.x, core.rs:192-194
-        acc[1] += o.y * r.d.y;
-        acc[2] += o.y * o.y;
-        acc[3] += x1 * x1;
+        double2 xo, o;
+        rosen_trial_pair(r.xp, r.d, step, xo, o, acc);
         st2<S>(x, i, xo);
         st2<S>(g, i, o);
     }
@@ -112,6 +117,67 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_trial(Rosen
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     stream_pairs<4, kUt>(n, op, acc);
     grid_reduce<4>(acc, ws, out);
+}
+
+// Write-free trial (lbfgsb200_probe_fn): the line search only ever looks at {f, g.d} of a trial point (and the
+// driver at g.g, x.x of the accepted one), so a probe reads xp and d and stores nothing — 2R instead of 2R 2W.
+// Same arithmetic, tile shape and grid as the fused trial: same bits.
+template <bool S>
+struct RosenProbeOp {
+    const double *xp, *d;
+    double step;
+    struct Regs { double2 xp, d; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const {
+        r.xp = ld2<S>(xp, i);
+        r.d = ld2<S>(d, i);
+    }
+    __device__ __forceinline__ void apply(Regs &r, int64_t, double (&acc)[4]) const {
+        double2 xo, o;
+        rosen_trial_pair(r.xp, r.d, step, xo, o, acc);
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[4]) const {}
+};
+template <bool S>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_probe(RosenProbeOp<S> op, int64_t n, ReduceWs ws, double *out) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    stream_pairs<4, kUt>(n, op, acc);
+    grid_reduce<4>(acc, ws, out);
+}
+
+// Accepted point + history update in one pass (lbfgsb200_commit_fn): x = xp + step*d and g = grad f(x) are
+// recomputed with the probe's arithmetic (same bits as the accepted probe saw), written once, and
+// s = x - xp, y = g - gp and IterationData::update's sums come out of the same registers — 3R 4W replacing the
+// last trial's 2W and k_history's 4R 2W.  Tile shape and accumulation order are k_history's (kUh, history_elem).
+template <bool S>
+struct RosenCommitOp {
+    const double *xp, *d, *gp;
+    double *x, *g, *s, *y;
+    double step, nstep;
+    struct Regs { double2 xp, d, gp; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const {
+        r.xp = ld2<S>(xp, i);
+        r.d = ld2<S>(d, i);
+        r.gp = ld2<S>(gp, i);
+    }
+    __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[5]) const {
+        double2 xo, o, so, yo;
+        xo.x = r.xp.x + step * r.d.x;                       // core.rs:156-157
+        xo.y = r.xp.y + step * r.d.y;
+        rosen_pair(xo.x, xo.y, o);
+        history_elem<true, false>(xo.x, r.xp.x, o.x, r.gp.x, 0.0, nstep, so.x, yo.x, acc);
+        history_elem<true, false>(xo.y, r.xp.y, o.y, r.gp.y, 0.0, nstep, so.y, yo.y, acc);
+        st2<S>(x, i, xo);
+        st2<S>(g, i, o);
+        st2<S>(s, i, so);
+        st2<S>(y, i, yo);
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[5]) const {}
+};
+template <bool S>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_commit(RosenCommitOp<S> op, int64_t n, ReduceWs ws, double *out) {
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    stream_pairs<5, kUh>(n, op, acc);
+    grid_reduce<5>(acc, ws, out);
 }
 
 // ---- Booth -----------------------------------------------------------------------------------
@@ -563,6 +629,26 @@ inline int stream_grid(const Objective *o, int64_t n, int U = kU) {
     return (int)tiles;
 }
 
+// The reduction workspace of one fused line-search launch.  Sharded over GPUs (set_shard gave us the communicator)
+// the kernel sums its scalars over the ranks in its own epilogue through the peer mailboxes — the same exchange,
+// and the same sequence counter, as the solver's own reducing kernels (every rank issues the same launches in the
+// same order) — so a trial on N GPUs costs no extra launch.
+inline bool sums_over_ranks(const Objective *o) {
+    return o->kind == OBJ_ROSENBROCK && o->comm && comm_size(o->comm) > 1 && comm_peer(o->comm) != nullptr;
+}
+inline ReduceWs fused_ws(Objective *o) {
+    ReduceWs ws = o->ws;
+    ws.peer = PeerCtx{};
+    if (sums_over_ranks(o)) {
+        ws.peer = *comm_peer(o->comm);
+        ws.peer.seq = ++*comm_peer_seq(o->comm);
+        ws.peer.extra[0] = ws.peer.extra[1] = nullptr;
+    }
+    return ws;
+}
+// 4 vectors in flight per trial; the same L2 rule as the solver's (working set vs 0.75 L2)
+inline bool rosen_streaming(const Objective *o, int64_t n) { return (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes; }
+
 int trial_impl(Objective *o, const double *xp, const double *d, double step, double *x, double *g, int64_t n,
                cudaStream_t stream, double *out) {
     if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
@@ -570,10 +656,31 @@ int trial_impl(Objective *o, const double *xp, const double *d, double step, dou
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     const int grid = stream_grid(o, n, kUt);
     const int threads = o->sequential ? 1 : kThreads;
-    // 4 vectors in flight per trial; the same L2 rule as the solver's (working set vs 0.75 L2)
-    const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
-    if (streaming) k_rosenbrock_trial<true><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, o->ws, out);
-    else k_rosenbrock_trial<false><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, o->ws, out);
+    if (rosen_streaming(o, n)) k_rosenbrock_trial<true><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, fused_ws(o), out);
+    else k_rosenbrock_trial<false><<<grid, threads, 0, stream>>>({xp, d, x, g, step}, n, fused_ws(o), out);
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
+int probe_impl(Objective *o, const double *xp, const double *d, double step, int64_t n, cudaStream_t stream, double *out) {
+    if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
+    if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    const int grid = stream_grid(o, n, kUt);
+    const int threads = o->sequential ? 1 : kThreads;
+    if (rosen_streaming(o, n)) k_rosenbrock_probe<true><<<grid, threads, 0, stream>>>({xp, d, step}, n, fused_ws(o), out);
+    else k_rosenbrock_probe<false><<<grid, threads, 0, stream>>>({xp, d, step}, n, fused_ws(o), out);
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
+int commit_impl(Objective *o, const double *xp, const double *d, const double *gp, double step, double bs_scale,
+                double *x, double *g, double *s, double *y, int64_t n, cudaStream_t stream, double *out) {
+    if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
+    if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    const int grid = stream_grid(o, n, kUh);
+    const int threads = o->sequential ? 1 : kThreads;
+    if (rosen_streaming(o, n)) k_rosenbrock_commit<true><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+    else k_rosenbrock_commit<false><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
@@ -584,8 +691,7 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
             if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;  // the reference indexes x[i+1] (lib.rs:86)
             const int grid = stream_grid(o, n, kUt);
             const int threads = o->sequential ? 1 : kThreads;
-            const bool streaming = (double)n * 16.0 > 0.75 * (double)o->dev.l2_bytes;
-            if (streaming) k_rosenbrock<true><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);
+            if (rosen_streaming(o, n)) k_rosenbrock<true><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);
             else k_rosenbrock<false><<<grid, threads, 0, stream>>>({x, g}, n, o->ws, fx);
             break;
         }
@@ -751,6 +857,35 @@ int lbfgsb200_objective_trial_eval(void *objective, const double *xp_dev, const 
     if (!objective || !xp_dev || !d_dev || !x_dev || !g_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
     return lb::trial_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, x_dev, g_dev, n_local,
                           (cudaStream_t)stream, out_dev);
+}
+int lbfgsb200_objective_probe(void *objective, const double *xp_dev, const double *d_dev, double step, int64_t n_local,
+                              void *stream, double *out_dev) {
+    if (!objective || !xp_dev || !d_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::probe_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, n_local, (cudaStream_t)stream, out_dev);
+}
+int lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev, double step,
+                               double bs_scale, double *x_dev, double *g_dev, double *s_dev, double *y_dev, int64_t n_local,
+                               void *stream, double *out_dev) {
+    if (!objective || !xp_dev || !d_dev || !gp_dev || !x_dev || !g_dev || !s_dev || !y_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::commit_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, gp_dev, step, bs_scale, x_dev, g_dev,
+                           s_dev, y_dev, n_local, (cudaStream_t)stream, out_dev);
+}
+int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fused_ops_t *out) {
+    lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
+    if (!o || !out) return LBFGSB200_ERR_INVALID_PARAM;
+    out->struct_size = (int64_t)sizeof(lbfgsb200_fused_ops_t);
+    out->trial = nullptr;
+    out->probe = nullptr;
+    out->commit = nullptr;
+    out->user = o;
+    out->flags = 0;
+    if (o->kind == lb::OBJ_ROSENBROCK) {
+        out->trial = lbfgsb200_objective_trial_eval;
+        out->probe = lbfgsb200_objective_probe;
+        out->commit = lbfgsb200_objective_commit;
+        if (lb::sums_over_ranks(o)) out->flags |= LBFGSB200_FUSED_SUMS_OVER_RANKS;
+    }
+    return 0;
 }
 void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
     lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);

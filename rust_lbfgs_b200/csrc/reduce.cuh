@@ -234,4 +234,18 @@ __device__ __forceinline__ void stream_pairs(int64_t n, Op &op, double (&acc)[NA
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.tail(n - 1, acc);
 }
 
+// IterationData::update for one element (src/lbfgs.rs:644-656, :670-673).  Shared by k_history and by the objectives'
+// commit kernels (lbfgsb200_commit_fn), so the fused and the unfused paths accumulate the same terms.
+template <bool DAMP, bool OWL>
+__device__ __forceinline__ void history_elem(double xi, double xpi, double gi, double gpi, double pgi, double nstep,
+                                             double &si, double &yi, double (&acc)[5]) {
+    si = xi - xpi;                                      // lbfgs.rs:644
+    yi = gi - gpi;                                      // :647 (raw gradients, also for OWL-QN: :529-530)
+    acc[0] += si * si;                                  // :645
+    acc[1] += yi * si;                                  // :653
+    acc[2] += yi * yi;                                  // :654
+    acc[3] += si * (-(OWL ? pgi : gi));                 // first trip of :587 with d = -g | -pg (core.rs:95-101)
+    if (DAMP) acc[4] += si * (gpi * nstep);             // :670-673, nstep = -step
+}
+
 }  // namespace lb

@@ -416,23 +416,26 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
         launch_dots(L, g, want_gd ? d_or_null : nullptr, x, n_, sl + 1);
         prof_end(LBFGSB200_K_DOTS, (want_gd ? 3.0 : 2.0) * vbytes);
     }
-    return finish_eval(false, dg_out);
+    return finish_eval(false, /*exchanged=*/true, dg_out);   // K2 / K3 summed over the ranks in their epilogue
 }
 
 // An Err from evaluate on any rank must be seen by every rank (replicated control flow): the flag is summed
 // over the ranks with the dot products.
 void Solver::post_eval_flag(int erc) {
-    scal_host_[kMaxAcc] = erc != 0 ? 1.0 : 0.0;
-    cudaMemcpyAsync(slot(SLOT_EVAL) + 7, scal_host_ + kMaxAcc, sizeof(double), cudaMemcpyHostToDevice, stream_);
+    scal_host_[kMaxAcc] = erc != 0 ? 1.0 : 0.0;   // every trial ends with a stream sync, so the word is free again
+    const cudaError_t e = cudaMemcpyAsync(slot(SLOT_EVAL) + 7, scal_host_ + kMaxAcc, sizeof(double),
+                                          cudaMemcpyHostToDevice, stream_);
+    if (e != cudaSuccess) cuda_fail(e, "cudaMemcpyAsync(H2D evaluate flag)");
 }
 
 // The scalar half of an evaluation: (optional) cross-rank sum, D2H of the slot, the one host sync per trial.
 // `fused`: the slot was written by the objective's fused trial (not by one of our reducing kernels).
-bool Solver::finish_eval(bool fused, double *dg_out) {
+bool Solver::finish_eval(bool fused, bool exchanged, double *dg_out) {
     const bool multi = comm_ && comm_size(comm_) > 1;
     double h[kMaxAcc];
-    if (fetch(SLOT_EVAL, kMaxAcc, h, /*ours=*/!fused) != 0) return false;
-    if (multi && h[7] != 0.0) return false;
+    if (last_status_ <= LBFGSB200_ERR_CUDA) return false;   // post_eval_flag failed
+    if (fetch(SLOT_EVAL, kMaxAcc, h, /*ours=*/exchanged) != 0) return false;
+    if (multi && !(fused && exchanged) && h[7] != 0.0) return false;
 
     neval_ += 1;
     if (owl_ && !fused) {
@@ -450,20 +453,25 @@ bool Solver::finish_eval(bool fused, double *dg_out) {
     return true;
 }
 
-// One line-search trial: take_line_step (core.rs:155-164) + evaluate (:119-132) + dg (:114-116).
-// With a fused trial evaluate registered (and no OWL-QN) this is ONE pass over xp and d.
+// One line-search trial: take_line_step (core.rs:155-164) + evaluate (:119-132) + dg (:114-116).  With the
+// objective's probe (+ commit) registered this is one WRITE-FREE pass over xp and d; with only its fused trial,
+// one pass that also writes x and g; otherwise K1 + evaluate + K2.  Never fused for OWL-QN.
 bool Solver::trial_point(const double *xp, double stp, double *dg_out) {
     const double vbytes = 8.0 * (double)n_;
     double *x = xbuf_[cur_x_];
-    if (trial_eval_ && !owl_) {
-        prof_begin(LBFGSB200_K_TRIAL_EVAL);
-        const int erc = trial_eval_(trial_user_, xp, d_, stp, x, gbuf_[cur_g_], n_, (void *)stream_, slot(SLOT_EVAL));
-        prof_end(LBFGSB200_K_TRIAL_EVAL, 4.0 * vbytes);
+    if (use_probe() || use_trial()) {
+        const bool probe = use_probe();
+        const int kind = probe ? LBFGSB200_K_PROBE : LBFGSB200_K_TRIAL_EVAL;
+        prof_begin(kind);
+        const int erc = probe ? fused_.probe(fused_.user, xp, d_, stp, n_, (void *)stream_, slot(SLOT_EVAL))
+                              : fused_.trial(fused_.user, xp, d_, stp, x, gbuf_[cur_g_], n_, (void *)stream_, slot(SLOT_EVAL));
+        prof_end(kind, (probe ? 2.0 : 4.0) * vbytes);
         launch_counter_ += 1;
         const bool multi = comm_ && comm_size(comm_) > 1;
-        if (erc != 0 && !multi) return false;
-        if (multi) post_eval_flag(erc);
-        return finish_eval(true, dg_out);
+        const bool exchanged = !multi || fused_exchanges();
+        if (erc != 0 && exchanged) return false;      // single GPU, or "fails on every rank or on none"
+        if (multi && !exchanged) post_eval_flag(erc);
+        return finish_eval(true, exchanged, dg_out);
     }
     Launch L = launch_cfg();
     prof_begin(LBFGSB200_K_TRIAL);
@@ -539,27 +547,49 @@ bool Solver::is_converged(int *stop_status) {
 }
 
 // ---- the update chain of one iteration: history (+ damping) + two-loop ------------------------------------------
-int Solver::enqueue_update(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last) {
-    // Everything here is enqueued without a host round trip: y.s, y.y, gamma and the damping branch are consumed
-    // on the device, and the host checks the history sums (`x not changed` / `gx not changed`) when it reads the
-    // final dot products.
+// Everything here is enqueued without a host round trip: y.s, y.y, gamma and the damping branch are consumed
+// on the device, and the host checks the history sums (`x not changed` / `gx not changed`) when it reads the
+// final dot products.
+//
+// IterationData::update (src/lbfgs.rs:640-692).  With the objective's probe + commit registered the accepted point
+// has not been written yet: the commit materialises x and g (from xp, d and the accepted trial's step) and forms
+// s, y and the history sums in the same pass; otherwise k_history reads x, xp, g, gp.
+int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp, double step_eval) {
     const int64_t slot_new = end_;
     const bool damping = p_.damping != 0;
     const double vbytes = 8.0 * (double)n_;
-    const double *x = xbuf_[cur_x_];
-    const double *g = gbuf_[cur_g_];
     double *hist = slot(SLOT_HIST);   // {s.s, y.s, y.y, s.(-g | -pg), s.Bs}
-    prof_begin(LBFGSB200_K_HISTORY);
-    launch_history(L, x, xp, g, gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_, damping, hist);
-    prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
-    int rc = reduce_across_ranks(SLOT_HIST, 5);
+    int rc = 0;
+    if (use_probe()) {
+        prof_begin(LBFGSB200_K_COMMIT);
+        const int erc = fused_.commit(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
+                                      Y_[slot_new], n_, (void *)L.stream, hist);
+        prof_end(LBFGSB200_K_COMMIT, 7.0 * vbytes);
+        launch_counter_ += 1;
+        if (erc != 0) return fail(erc <= LBFGSB200_ERR_CUDA ? erc : LBFGSB200_ERR_EVALUATE, "the objective's commit failed");
+        rc = reduce_across_ranks(SLOT_HIST, 5, /*ours=*/fused_exchanges());
+    } else {
+        prof_begin(LBFGSB200_K_HISTORY);
+        launch_history(L, xbuf_[cur_x_], xp, gbuf_[cur_g_], gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_,
+                       damping, hist);
+        prof_end(LBFGSB200_K_HISTORY, (owl_ ? 7.0 : 6.0) * vbytes);
+        rc = reduce_across_ranks(SLOT_HIST, 5);
+    }
     if (rc != 0) return fail(rc, "ncclAllReduce failed");
     if (damping) {  // :664-689, decided inside the kernel (case 1 rewrites y, otherwise it exits at once)
         prof_begin(LBFGSB200_K_DAMP);
         launch_damp(L, Y_[slot_new], gp, n_, -step_, hist);
         prof_end(LBFGSB200_K_DAMP, 0.0);
     }
+    return 0;
+}
 
+int Solver::enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, int *so_last) {
+    (void)gp;
+    const double vbytes = 8.0 * (double)n_;
+    const double *g = gbuf_[cur_g_];
+    double *hist = slot(SLOT_HIST);
+    int rc = 0;
     // lbfgs_two_loop_recursion, src/lbfgs.rs:569-604, one fused kernel per trip (end = (end + 1) % m, :575)
     int64_t j = (end_ + 1) % m_;
     const double *red_in = hist + 3;              // s_new . (-g), produced by the history kernel
@@ -599,12 +629,12 @@ int Solver::enqueue_update(const Launch &L, const double *xp, const double *gp, 
     return 0;
 }
 
-// CUDA-graph replay of enqueue_update for the launch-bound regime.  The kernel arguments of the chain depend only
+// CUDA-graph replay of enqueue_two_loop for the launch-bound regime.  The kernel arguments of the chain depend only
 // on the ring position (which s/y slots), the x/g buffer parity and — fixed for a solver — the option set, so
 // after the history ring is full there are at most 2m distinct chains; each is captured once and then replayed
 // with a single cudaGraphLaunch (1 + 2m kernels cost ~4.5 us of CPU launch time each otherwise).
 bool Solver::graph_eligible(int64_t bound) const {
-    if (!graphs_enabled_ || timing_ || sequential_ || p_.damping != 0) return false;   // damping passes -step by value
+    if (!graphs_enabled_ || timing_ || sequential_) return false;
     if (comm_ && comm_size(comm_) > 1) return false;                                   // exchange sequence numbers are by value
     if (bound != m_) return false;                                                     // ring still filling
     // capturing + instantiating one chain costs about as much as 6 iterations of direct launches and saves
@@ -613,16 +643,18 @@ bool Solver::graph_eligible(int64_t bound) const {
     return n_ <= kGraphMaxN;
 }
 
-int Solver::update_graphed(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last) {
+int Solver::two_loop_graphed(const Launch &L, const double *gp, int64_t bound, int *so_last) {
     if (!cap_stream_) {
         if (cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
             graphs_enabled_ = false;
-            return enqueue_update(L, xp, gp, bound, so_last);
+            return enqueue_two_loop(L, gp, bound, so_last);
         }
-        graphs_.assign((size_t)(2 * m_), GraphEntry{});
+        graphs_.assign((size_t)(4 * m_), GraphEntry{});
     }
-    GraphEntry &ge = graphs_[(size_t)(end_ * 2 + cur_x_)];
+    // a chain bakes in the ring position and BOTH buffer parities (x/xp and g/gp flip together in propagate, but
+    // finish() re-homes x alone)
+    GraphEntry &ge = graphs_[(size_t)(end_ * 4 + cur_x_ * 2 + cur_g_)];
     if (!ge.exec) {
         const lbfgsb200_profile_t before = prof_;
         const int64_t launches_before = launch_counter_;
@@ -630,7 +662,7 @@ int Solver::update_graphed(const Launch &L, const double *xp, const double *gp, 
         Lc.stream = cap_stream_;
         cudaGraph_t graph = nullptr;
         bool ok = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-        int rc = ok ? enqueue_update(Lc, xp, gp, bound, &ge.so_last) : 0;
+        int rc = ok ? enqueue_two_loop(Lc, gp, bound, &ge.so_last) : 0;
         if (ok) ok = cudaStreamEndCapture(cap_stream_, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
         if (ok) ok = cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess;
         if (graph) cudaGraphDestroy(graph);
@@ -646,7 +678,7 @@ int Solver::update_graphed(const Launch &L, const double *xp, const double *gp, 
             cudaGetLastError();
             ge.exec = nullptr;
             graphs_enabled_ = false;
-            return enqueue_update(L, xp, gp, bound, so_last);
+            return enqueue_two_loop(L, gp, bound, so_last);
         }
     }
     if (cudaGraphLaunch(ge.exec, stream_) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGraphLaunch");
@@ -704,9 +736,11 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         launch_orthant(L, wp_, xp, pg_, n_);
         prof_end(LBFGSB200_K_ORTHANT, 2.0 * vbytes + (double)n_);
     }
-    double stp = 0.0;
+    double stp = 0.0, stp_eval = 0.0;   // stp_eval: the step of the last EVALUATED trial, i.e. where x is (line.rs:396-398
+                                        // leaves `stp` one update ahead when the search runs out of trials)
     while (ls.next_trial(&stp)) {
         double dg = 0.0;
+        stp_eval = stp;
         const bool ok = trial_point(xp, stp, &dg);
         if (!ok && last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;  // CUDA / NCCL failure is fatal
         ls.feed(ok, fx_, dg);
@@ -732,8 +766,10 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     const int64_t bound = (m_ < k_ - 1) ? m_ : (k_ - 1);
     int so_last = SLOT_LOOP_A;
     int rc = 0;
-    if (graph_eligible(bound)) rc = update_graphed(L, xp, gp, bound, &so_last);
-    else rc = enqueue_update(L, xp, gp, bound, &so_last);
+    rc = enqueue_history(L, xp, gp, stp_eval);
+    if (rc != 0) return rc;
+    if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
+    else rc = enqueue_two_loop(L, gp, bound, &so_last);
     if (rc != 0) return rc;
     end_ = (end_ + 1) % m_;
     // the one host round trip of the update: the history sums and the final dot products together

@@ -66,8 +66,13 @@ class Solver {
     double *spare_x() const { return x_spare_; }   // an n-vector of the arena for the host-buffer entry points
     const std::string &error() const { return err_; }
 
-    // optional fused trial evaluate (lbfgsb200_trial_eval_fn); ignored for OWL-QN
-    void set_trial_evaluate(lbfgsb200_trial_eval_fn fn, void *user) { trial_eval_ = fn; trial_user_ = user; }
+    // optional fused line-search entries of the objective (lbfgsb200_fused_ops_t); ignored for OWL-QN
+    void set_trial_evaluate(lbfgsb200_trial_eval_fn fn, void *user) {
+        fused_ = lbfgsb200_fused_ops_t{};
+        fused_.trial = fn;
+        fused_.user = user;
+    }
+    void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; }
 
     // timing: 0 = off, 1 = every kernel kind, otherwise a mask: bit (1 + kind) times LBFGSB200_K_<kind> only
     void profile_enable(int timing) { timing_ = timing != 0; timing_mask_ = (timing == 1) ? ~0u : ((unsigned)timing >> 1); }
@@ -82,8 +87,12 @@ class Solver {
     int fail(int status, const char *msg);
     int cuda_fail(cudaError_t e, const char *what);
     bool evaluate_point(const double *d_or_null, double *dg_out);  // evaluate + K2/K3 + allreduce + sync
-    bool trial_point(const double *xp, double stp, double *dg_out); // K1 + evaluate_point, or the fused callback
-    bool finish_eval(bool fused, double *dg_out);                  // allreduce + D2H + sync of SLOT_EVAL
+    bool trial_point(const double *xp, double stp, double *dg_out); // K1 + evaluate_point, or the fused callbacks
+    // allreduce (unless `exchanged`: the producer already summed over the ranks) + D2H + sync of SLOT_EVAL
+    bool finish_eval(bool fused, bool exchanged, double *dg_out);
+    bool use_probe() const { return fused_.probe && fused_.commit && !owl_; }
+    bool use_trial() const { return fused_.trial && !owl_; }
+    bool fused_exchanges() const { return (fused_.flags & LBFGSB200_FUSED_SUMS_OVER_RANKS) != 0; }
     void post_eval_flag(int erc);
     int fetch(int s, int count, double *host, bool ours = true);   // allreduce + D2H + sync of a slot
     int fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2);  // two reduced slots, one sync
@@ -91,10 +100,12 @@ class Solver {
     int reduce_across_ranks(int s, int count, bool ours = true);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
     Launch launch_cfg();
-    // history (+ damping) + two-loop of one iteration, enqueued on L.stream; *so_last = slot of the final dots
-    int enqueue_update(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last);
+    // history (or the objective's commit) of one iteration, enqueued on L.stream
+    int enqueue_history(const Launch &L, const double *xp, const double *gp, double step_eval);
+    // (+ damping) + two-loop of one iteration, enqueued on L.stream; *so_last = slot of the final dots
+    int enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, int *so_last);
     bool graph_eligible(int64_t bound) const;
-    int update_graphed(const Launch &L, const double *xp, const double *gp, int64_t bound, int *so_last);
+    int two_loop_graphed(const Launch &L, const double *gp, int64_t bound, int *so_last);
     void drop_graphs();
 
     // timing instrumentation
@@ -134,8 +145,7 @@ class Solver {
     // host scalars
     lbfgsb200_eval_fn eval_ = nullptr;
     void *eval_user_ = nullptr;
-    lbfgsb200_trial_eval_fn trial_eval_ = nullptr;
-    void *trial_user_ = nullptr;
+    lbfgsb200_fused_ops_t fused_{};
     bool built_ = false;
     double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point
     double dginit_ = 0.0;                      // g.d (pg.d) for the next line search

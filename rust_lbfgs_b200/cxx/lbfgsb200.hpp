@@ -106,6 +106,17 @@ class Objective {
         Objective o; check(lbfgsb200_objective_glm(device, kind, X_dev, y_dev, nrow, ncol, &o.h_)); return o;
     }
     lbfgsb200_objective_t *handle() const { return h_; }
+    // multi-GPU: see lbfgsb200_objective_set_shard (offsets: Lennard-Jones only)
+    void shard(lbfgsb200_comm_t *comm, const int64_t *shard_offsets = nullptr) const {
+        check(lbfgsb200_objective_set_shard(h_, comm, shard_offsets));
+    }
+    // what the objective offers beyond evaluate (probe + commit, fused trial); fused = false: nothing
+    lbfgsb200_fused_ops_t fused_ops(bool fused) const {
+        lbfgsb200_fused_ops_t ops{};
+        ops.struct_size = (int64_t)sizeof(ops);
+        if (fused) check(lbfgsb200_objective_fused_ops(h_, &ops));
+        return ops;
+    }
 
   private:
     static void check(int rc) { if (rc != 0) throw Error(rc, "creating a device objective failed (no CUDA device?)"); }
@@ -188,6 +199,7 @@ class Lbfgs {
     Lbfgs &with_shard(lbfgsb200_comm_t *comm, int64_t n_global, int64_t global_offset) {
         comm_ = comm; n_global_ = n_global; goff_ = global_offset; return *this;
     }
+    // false: line-search trials as K1 + evaluate + K2 even if the objective offers probe + commit / a fused trial
     Lbfgs &with_fused_trial(bool fused) { fused_ = fused; return *this; }
 
     // minimize, src/lbfgs.rs:399-421.  x_dev: n doubles of device memory, updated in place.
@@ -199,8 +211,9 @@ class Lbfgs {
     Report minimize(double *x_dev, int64_t n, const Objective &objective, ProgressFn progress = nullptr) const {
         Handle h(*this, n);
         lbfgsb200_objective_set_reduction(objective.handle(), (int)p_.reduction);
-        if (fused_ && lbfgsb200_objective_has_trial_eval(objective.handle()))
-            lbfgsb200_set_trial_evaluate(h.s, lbfgsb200_objective_trial_eval, objective.handle());
+        if (comm_) objective.shard(comm_);
+        const lbfgsb200_fused_ops_t ops = objective.fused_ops(fused_);
+        lbfgsb200_set_fused_ops(h.s, &ops);
         return run(h.s, x_dev, lbfgsb200_objective_eval, objective.handle(), progress);
     }
     // The reference's exact shape: x is a HOST slice (`minimize(&mut x, ..)`); copied to the device, solved on
@@ -208,11 +221,11 @@ class Lbfgs {
     Report minimize(std::vector<double> &x, const Objective &objective, ProgressFn progress = nullptr) const {
         lbfgsb200_report_t rep{};
         lbfgsb200_objective_set_reduction(objective.handle(), (int)p_.reduction);
-        const bool fused = fused_ && lbfgsb200_objective_has_trial_eval(objective.handle());
+        if (comm_) objective.shard(comm_);
+        const lbfgsb200_fused_ops_t ops = objective.fused_ops(fused_);
         const int64_t n = (int64_t)x.size();
         int st = lbfgsb200_minimize_host_ex(&p_, x.data(), n, n_global_ > 0 ? n_global_ : n, goff_, device_, comm_,
-                                            lbfgsb200_objective_eval, objective.handle(),
-                                            fused ? lbfgsb200_objective_trial_eval : nullptr, fused ? objective.handle() : nullptr,
+                                            lbfgsb200_objective_eval, objective.handle(), &ops,
                                             progress ? tramp_progress : nullptr, progress ? &progress : nullptr, &rep);
         Report r = convert(rep, st);
         if (st < 0) throw Error(st, "minimize failed (status " + std::to_string(st) + ")", r);
@@ -279,8 +292,9 @@ class LbfgsState {
   public:
     LbfgsState(const Lbfgs &b, double *x_dev, int64_t n, const Objective &objective) : h_(b, n) {
         lbfgsb200_objective_set_reduction(objective.handle(), (int)b.p_.reduction);
-        if (b.fused_ && lbfgsb200_objective_has_trial_eval(objective.handle()))
-            lbfgsb200_set_trial_evaluate(h_.s, lbfgsb200_objective_trial_eval, objective.handle());
+        if (b.comm_) objective.shard(b.comm_);
+        const lbfgsb200_fused_ops_t ops = objective.fused_ops(b.fused_);
+        lbfgsb200_set_fused_ops(h_.s, &ops);
         int st = lbfgsb200_build(h_.s, x_dev, lbfgsb200_objective_eval, objective.handle());
         if (st != 0) throw Error(st, lbfgsb200_last_error(h_.s));
     }

@@ -9,6 +9,8 @@ from . import _lib
 
 
 class _Builtin:
+    _auto_shard = False   # shard-local objectives: a sharded solve hands them its communicator by itself
+
     def __init__(self):
         self._handles = {}
         self._shard = None   # (comm, offsets or None)
@@ -38,12 +40,19 @@ class _Builtin:
     def _eval_ptr(self):
         return C.cast(_lib.lib().lbfgsb200_objective_eval, C.c_void_p)
 
-    def _trial_eval_ptr(self, device):
-        """The lbfgsb200_trial_eval_fn of this objective (fused trial step + evaluate + dots), or None."""
-        L = _lib.lib()
-        if L.lbfgsb200_objective_has_trial_eval(self._user_ptr(device)) != 1:
+    def _fused_ops(self, device, mode=True):
+        """lbfgsb200_fused_ops_t of this objective, or None.  mode True / "probe": everything it offers (write-free
+        probes + one commit per iteration when it has them); "trial": only the one-pass trial that writes x and g."""
+        ops = _lib.FusedOps()
+        st = _lib.lib().lbfgsb200_objective_fused_ops(self._user_ptr(device), C.byref(ops))
+        if st != 0:
+            raise RuntimeError(f"lbfgsb200_objective_fused_ops failed: {_lib.STATUS_NAMES.get(st, st)}")
+        if mode == "trial":
+            ops.probe = None
+            ops.commit = None
+        if not (ops.trial or ops.probe):
             return None
-        return C.cast(L.lbfgsb200_objective_trial_eval, C.c_void_p)
+        return ops
 
     def _set_reduction(self, device, reduction):
         st = _lib.lib().lbfgsb200_objective_set_reduction(self._user_ptr(device), reduction)
@@ -75,7 +84,9 @@ class _Builtin:
 
 
 class Rosenbrock(_Builtin):
-    """default_evaluate(), src/lib.rs:79-94 (len(x) must be even)."""
+    """default_evaluate(), src/lib.rs:79-94 (len(x) must be even).  Shard-local; with the solve's communicator its
+    fused line-search kernels sum their scalars over the ranks in their own epilogue."""
+    _auto_shard = True
 
     def _create(self, L, device, out):
         return L.lbfgsb200_objective_rosenbrock(device, C.byref(out))

@@ -32,6 +32,7 @@ for v in "$@"; do
     vF) build vF 9 1 4 256 9;;
     vG) build vG 8 1 4 256 3;;
     vH) build vH 8 1 4 256 4;;
+    x-*) IFS=- read -r _ u uh ut <<< "$v"; build "$v" "$u" 1 "$uh" 256 "$ut";;   # x-<U>-<UH>-<UT>
   esac
 done
 ls -la ../../build/variants

@@ -168,29 +168,60 @@ def test_error_status_bit_exact(oracle):
             assert np.array_equal(a["x"], c["x"]) and a["fx"] == c["fx"] and a["ncall"] == c["ncall"]
 
 
-# ---- fused trial == unfused trial, bit for bit -----------------------------------------------------------------------
-@pytest.mark.parametrize("n", [2, 100, 2050, 1 << 20, (1 << 22) + 2])
-def test_fused_trial_matches_unfused_bitwise(n):
-    """lbfgsb200_trial_eval_fn (one pass) vs K1 + evaluate + K2 (three passes): same tiles, same trees."""
-    iters = 40 if n <= (1 << 20) else 12
-    a = gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(True), rosenbrock_x0(n), R.Rosenbrock(),
-                     record_x=n <= 4096)
-    b = gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(False), rosenbrock_x0(n), R.Rosenbrock(),
-                     record_x=n <= 4096)
-    assert a["status_name"] == b["status_name"] and len(a["trace"]) == len(b["trace"]) > 3
+# ---- probe + commit == fused trial == unfused trial, bit for bit -------------------------------------------------
+def _same_traces(a, b, what):
+    assert a["status_name"] == b["status_name"] and len(a["trace"]) == len(b["trace"]) > 3, what
     for s, t in zip(a["trace"], b["trace"]):
         for key in ("neval", "ncall", "fx", "xnorm", "gnorm", "step"):
-            assert s[key] == t[key], (n, s["niter"], key, s[key], t[key])
+            assert s[key] == t[key], (what, s["niter"], key, s[key], t[key])
         if "x" in s:
-            assert np.array_equal(s["x"], t["x"]) and np.array_equal(s["gx"], t["gx"])
-    assert np.array_equal(a["x"], b["x"])
+            assert np.array_equal(s["x"], t["x"]) and np.array_equal(s["gx"], t["gx"]), (what, s["niter"])
+    assert np.array_equal(a["x"], b["x"]), what
+
+
+def perturbed_x0(n, seed=1234):
+    """x0 = (-1.2, 1) repeated plus U(-0.1, 0.1), seed 1234 — no two pairs are alike."""
+    return rosenbrock_x0(n) + np.random.default_rng(seed).uniform(-0.1, 0.1, n)
+
+
+@pytest.mark.parametrize("n", [2, 100, 2050, 1 << 20, (1 << 22) + 2])
+def test_fused_modes_match_unfused_bitwise(n):
+    """Write-free probes + one commit per iteration (lbfgsb200_probe_fn / _commit_fn), the one-pass trial
+    (lbfgsb200_trial_eval_fn) and K1 + evaluate + K2 + K5 (unfused): same tiles, same trees, same bits — on data
+    where every pair differs, so a wrong tile offset cannot hide."""
+    iters = 40 if n <= (1 << 20) else 12
+    x0 = perturbed_x0(n)
+    runs = {mode: gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(mode), x0, R.Rosenbrock(),
+                               record_x=n <= (1 << 20))
+            for mode in ("probe", "trial", False)}
+    _same_traces(runs["probe"], runs[False], f"n={n} probe vs unfused")
+    _same_traces(runs["trial"], runs[False], f"n={n} trial vs unfused")
+
+
+@pytest.mark.parametrize("algo", ["MoreThuente", "BacktrackingArmijo", "BacktrackingWolfe", "BacktrackingStrongWolfe"])
+def test_probe_commit_all_linesearches_and_damping_bitwise(algo):
+    """The commit uses the step of the last EVALUATED trial (and -step_returned for the damping sum): every line
+    search, with and without Powell damping, including searches that run out of trials (max_linesearch = 3)."""
+    x0 = perturbed_x0(3000, seed=7)
+    for damp in (False, True):
+        for maxls in (20, 3):
+            mk = lambda mode: (R.lbfgs().with_linesearch_algorithm(algo).with_damping(damp).with_max_linesearch(maxls)
+                               .with_max_iterations(30).with_fused_trial(mode))
+            a = gpu_minimize(mk("probe"), x0, R.Rosenbrock())
+            b = gpu_minimize(mk(False), x0, R.Rosenbrock())
+            _same_traces(a, b, f"{algo} damping={damp} max_linesearch={maxls}")
 
 
 def test_fused_trial_sequential_bit_exact(oracle):
     ref = oracle_run(oracle, rosenbrock_x0(1000), "rosenbrock")
-    for fused in (True, False):
+    for fused in ("probe", "trial", False):
         got = gpu_minimize(seq().with_fused_trial(fused), rosenbrock_x0(1000), R.Rosenbrock())
         assert_bit_identical(ref, got, f"fused={fused}")
+    x0 = perturbed_x0(514, seed=3)
+    ref = oracle_run(oracle, x0, "rosenbrock", damping=1, ls_algorithm=3, max_iterations=40)
+    got = gpu_minimize(seq().with_linesearch_algorithm("BacktrackingStrongWolfe").with_damping(True).with_max_iterations(40)
+                       .with_fused_trial("probe"), x0, R.Rosenbrock())
+    assert_bit_identical(ref, got, "probe + commit, damping")
 
 
 def test_fused_trial_kernel_direct(oracle):
@@ -219,6 +250,32 @@ def test_fused_trial_kernel_direct(oracle):
         o = host(out)
         for got, want in ((o[0], fr), (o[1], float(gr @ d)), (o[2], float(gr @ gr)), (o[3], float(xr @ xr))):
             assert abs(got - want) <= 1e-13 * max(abs(want), float(np.abs(gr).max() * np.abs(d).max())), (n, got, want)
+        # the write-free probe: the same four sums, bit for bit, and no stores
+        out2 = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+        ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), step, n, stream(), out2.data_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(host(out2)[:4], o[:4]), n
+        # the commit: x, g as the trial wrote them; s = x - xp, y = g - gp bit-exact; the sums of lbfgsb200_history_update
+        gp = rng.standard_normal(n)
+        gpd = dev(gp)
+        x2, g2, s2, y2 = (torch.empty(n, dtype=torch.float64, device="cuda:0") for _ in range(4))
+        out3 = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+        ck(L.lbfgsb200_objective_commit(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), gpd.data_ptr(), step, -0.41,
+                                        x2.data_ptr(), g2.data_ptr(), s2.data_ptr(), y2.data_ptr(), n, stream(), out3.data_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(host(x2), xr) and np.array_equal(host(g2), gr)
+        assert np.array_equal(host(s2), xr - xp) and np.array_equal(host(y2), gr - gp)
+        s3, y3 = torch.empty_like(s2), torch.empty_like(y2)
+        h = (C.c_double * 5)()
+        ck(L.lbfgsb200_history_update(s3.data_ptr(), y3.data_ptr(), xd.data_ptr(), xpd.data_ptr(), gd.data_ptr(), gpd.data_ptr(),
+                                      None, n, 0.41, 1, stream(), h))
+        assert np.array_equal(host(s3), host(s2)) and np.array_equal(host(y3), host(y2))
+        assert list(h) == list(host(out3)[:5]), (n, list(h), host(out3)[:5])
     lj = R.LennardJones()
+    ops = R._lib.FusedOps()
+    ck(L.lbfgsb200_objective_fused_ops(lj._user_ptr(0), C.byref(ops)))
+    assert not ops.trial and not ops.probe and not ops.commit
+    ck(L.lbfgsb200_objective_fused_ops(obj._user_ptr(0), C.byref(ops)))
+    assert ops.trial and ops.probe and ops.commit and ops.flags == 0
     assert L.lbfgsb200_objective_has_trial_eval(lj._user_ptr(0)) == 0
     assert L.lbfgsb200_objective_has_trial_eval(obj._user_ptr(0)) == 1

@@ -396,3 +396,61 @@ def test_full_size_owlqn_n1e8_follows_the_reference_algorithm(oracle):
     st.close()
     print("OWL-QN n=1e8: worst relative deviation over", len(ref), "iterations:", worst)
     assert len(ref) == iters and worst <= 1e-9
+
+
+# ---- non-degenerate data on the production (tiled, multi-CTA, grid-stride) path ---------------------------------------
+def perturbed_x0(n, seed=1234):
+    """x0 = (-1.2, 1) repeated plus U(-0.1, 0.1), seed 1234 — no two pairs are alike, so a kernel
+    that read the wrong tile or offset cannot produce the right numbers."""
+    return rosenbrock_x0(n) + np.random.default_rng(seed).uniform(-0.1, 0.1, n)
+
+
+@pytest.mark.parametrize("n,iters", [(100_000, 60), (4_000_000, 25)])
+@pytest.mark.parametrize("fused", ["probe", False])
+def test_perturbed_x0_tree_mode_vs_oracle_pair(oracle, n, iters, fused):
+    """TREE-mode (production) solves beyond one tile against the faithful + compensated oracle pair: 25 / 782 CTAs'
+    worth of tiles, grid-stride at 4e6, every element different.  Identical status, iteration and evaluation
+    counts; x and fx within 1e-10 (first 50 iterations) of the faithful oracle, or 100x the drift between the two
+    CPU summation orders where that is larger."""
+    x0 = perturbed_x0(n)
+    ref, alt = oracle_pair(oracle, x0, "rosenbrock", max_iterations=iters)
+    got = gpu_minimize(R.lbfgs().with_max_iterations(iters).with_fused_trial(fused), x0, R.Rosenbrock())
+    worst = compare_traces(ref, got, alt=alt)
+    print(f"n={n} fused={fused}: worst rel err {worst}")
+    assert len(got["trace"]) == iters
+    # and against the compensated oracle alone (the more accurate of the two CPU orders), same bar
+    for a, b in zip(alt["trace"], got["trace"]):
+        if a["ncall"] != b["ncall"]:
+            break
+        assert np.max(np.abs(a["x"] - b["x"])) <= 1e-10 * np.max(np.abs(a["x"])) * (1.0 if a["niter"] <= 50 else 100.0), a["niter"]
+
+
+def test_perturbed_x0_n1e8_vs_compensated_oracle(oracle):
+    """BASELINE configs[1]'s size with non-degenerate data: 6 L-BFGS iterations at n = 1e8 from the perturbed x0
+    against the oracle with compensated sums (the faithful oracle's sequential sums are themselves off by ~1e-9
+    at this size).  Identical evaluation counts in every iteration; fx, ||x||, ||g||, step within
+    1e-10; the final x within 1e-10 element-wise (relative to max|x|)."""
+    import torch
+    n, iters = 100_000_000, 7
+    free, _ = torch.cuda.mem_get_info()
+    if free < 20 * 8 * n * 1.05:
+        pytest.skip("not enough free HBM")
+    x0 = perturbed_x0(n)
+    ref = oracle.minimize(oracle.default_param(max_iterations=iters, reduction_mode=1), x0.copy(),
+                          oracle.Objective.builtin("rosenbrock", 1))
+    x = torch.from_numpy(x0).to("cuda:0")
+    del x0
+    trace = []
+    rep = R.lbfgs().with_max_iterations(iters).minimize(
+        x, R.Rosenbrock(), lambda p: trace.append((p.niter, p.neval, p.ncall, p.fx, p.xnorm, p.gnorm, p.step)) and False)
+    assert rep.status_name == ref["status_name"] == "OK_MAX_ITERATIONS"
+    assert len(trace) == len(ref["trace"]) == iters
+    worst = 0.0
+    for got, t in zip(trace, ref["trace"]):
+        assert got[:3] == (t["niter"], t["neval"], t["ncall"]), (got[:3], t)
+        for a, b in zip(got[3:], (t["fx"], t["xnorm"], t["gnorm"], t["step"])):
+            worst = max(worst, abs(a - b) / abs(b))
+    xg = x.cpu().numpy()
+    ex = float(np.max(np.abs(xg - ref["x"])) / np.max(np.abs(ref["x"])))
+    print(f"n=1e8 perturbed x0: worst scalar deviation {worst:.3e}, final x deviation {ex:.3e}, evaluations {rep.neval}")
+    assert worst <= 1e-10 and ex <= 1e-10
