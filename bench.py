@@ -178,26 +178,53 @@ def isometric_oracle_trace(n_global, m, iters, owl_c=None, record_x=False):
     return r["trace"]
 
 
+def host_numa_cpus(local_rank):
+    """CPUs of the NUMA node the GPU hangs off (so pinned buffers and the launching thread are local to it)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        return sorted(cpus & allowed) or None
+    except Exception:
+        return None
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for the path.  The reference is Rust and this
-    image has no rustc/cargo, so it is the oracle port (oracle/lbfgs_oracle.cpp), single-threaded like the
-    reference (README.md:24-25: rayon/SIMD are unchecked TODOs).  Each step is one L-BFGS iteration on a
-    bounded sample n_sample of the n = 1e8 workload; the rate is normalised to n = 1e8."""
+    """--impl reference: the reference's own CPU algorithm for the path, on the QUOTED configuration (n = 1e8,
+    m = 6).  The reference is Rust and this image has no rustc/cargo, so it is the oracle port
+    (oracle/lbfgs_oracle.cpp), single-threaded like the reference (README.md:24-25: rayon/SIMD are unchecked
+    TODOs).  One step = one L-BFGS iteration at n = 1e8 (19 vectors x 0.8 GB = 15.2 GB of host RAM, about 5-8 s per
+    iteration); W warm-up and K timed iterations as asked, cut short (and `steps` says so) if the timed part would
+    exceed --ref-budget seconds.  Under torchrun only rank 0 runs; its sample is one GPU's shard (n = 1e8)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_sample = int(args.ref_n)
-    rate, dt, done = cpu_oracle_rate(n_sample, args.warmup, args.steps, m=args.m)
+    rate, dt, done = cpu_oracle_rate(n_sample, args.warmup, args.steps, m=args.m, budget_s=args.ref_budget)
     value = rate * n_sample / N_REF
-    sample = (f"Rosenbrock n={n_sample} (same x0 pattern, m={args.m}, MoreThuente), iterations "
-              f"{args.warmup + 1}..{args.warmup + done}; it/s scaled by n_sample/1e8")
+    world = max(1, args.gpus)
+    sample = (f"oracle (C++ port of the reference, 1 thread) Rosenbrock n={n_sample} (x0 = (-1.2, 1) repeated, m={args.m}, "
+              f"MoreThuente), iterations {args.warmup + 1}..{args.warmup + done}"
+              + ("" if n_sample == N_REF else "; it/s scaled by n_sample/1e8"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done * (N_REF / n_sample),
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_per_gpu": N_REF, "n_global": N_REF, "m": args.m, "linesearch": "MoreThuente",
-                   "reference_arm": "CPU oracle port (the reference is Rust; no rustc here), 1 thread as the reference",
-                   "n_sample": n_sample},
+        "config": workload_config(N_REF, N_REF * world, args.m),
+        "run": {"n_timed": n_sample, "seconds_timed": dt, "steps_requested": args.steps,
+                "reference_arm": "CPU oracle port (the reference is Rust; no rustc here), 1 thread as the reference",
+                "note": None if world == 1 else "timed at one GPU's shard (n = 1e8): the metric is normalised to n = 1e8 "
+                        "and the CPU cost per element does not depend on n"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,7 +232,156 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def workload_config(n_local, n_global, m):
+    """The `config` block: identical in both arms (everything that varies from run to run lives in `run`)."""
+    return {"workload": WORKLOAD if (n_local == N_REF and m == 6) else
+            f"Rosenbrock n={n_local} f64 per GPU, m={m}, MoreThuente, device-resident evaluate",
+            "n_per_gpu": n_local, "n_global": n_global, "m": m, "linesearch": "MoreThuente",
+            "l2_policy": "inputs larger than L2 (19 vectors x 0.8 GB vs 126 MB)"}
+
+
 # ---------------------------------------------------------------------------------------------------
+def timed_iterations(R, D, dev, comm, world, n_local, m, K, W, fused, barrier, sampler=None, dom="backward",
+                     profile_pass=0):
+    """W warm-up + K timed L-BFGS iterations on a device-resident x0 = (-1.2, 1) repeated; CUDA events on the
+    solver's stream (torch's current stream), max over ranks.  Returns a dict of raw measurements."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    n_global, goff = n_local * world, rank * n_local
+    b = R.lbfgs().with_m(m).with_fused_trial(fused)
+    if comm is not None:
+        b = b.with_shard(comm, n_global, goff)
+    x = torch.empty(n_local, dtype=torch.float64, device=dev)
+    x[0::2] = -1.2
+    x[1::2] = 1.0
+    obj = R.Rosenbrock()
+    state = b.build(x, obj)
+    state.propagate()                       # propagate #1 is the reference's no-op (src/lbfgs.rs:507-510)
+    for _ in range(W):
+        state.propagate()
+    # CUDA events around the dominant kernel only inside the timed region (events around every launch cost
+    # ~2 % at n = 1e8); the other kernels are timed in a separate pass after it
+    state.profile_enable(True, kinds=[dom])
+    state.profile_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    wall_begin = time.time()
+    ev0.record()
+    seen = []
+    for _ in range(K):
+        p = state.propagate()
+        seen.append((p.niter, p.ncall, p.fx, p.xnorm, p.gnorm, p.step))
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_end = time.time()
+    barrier()
+    clocks = sampler.stop(wall_begin, wall_end) if sampler is not None else None
+    out = {"ms_total": D.max_over_ranks(ev0.elapsed_time(ev1)), "prof": state.profile(), "final": state.report(),
+           "seen": seen, "clocks": clocks, "prof_all": None, "profile_iterations": profile_pass,
+           "transport": comm.transport if comm is not None else None}
+    if profile_pass:   # per-kernel profile pass (NOT part of `value`): more iterations with events around every launch
+        state.profile_enable(True)
+        state.profile_reset()
+        for _ in range(profile_pass):
+            state.propagate()
+        out["prof_all"] = state.profile()
+    state.finish()
+    state.close()
+    obj.close()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def isometric_parity(seen, n_global, m, iters):
+    """The timed trajectory against the reference algorithm on the isometric 2-variable image of the workload."""
+    try:
+        ref = {t["niter"]: t for t in isometric_oracle_trace(n_global, m, iters)}
+        worst, same = 0.0, True
+        for (it, nc, fx, xn, gn, stp) in seen:
+            t = ref.get(it)
+            if t is None or t["ncall"] != nc:
+                same = False
+                break
+            for a, b in ((fx, t["fx"]), (xn, t["xnorm"]), (gn, t["gnorm"]), (stp, t["step"])):
+                worst = max(worst, abs(a - b) / max(abs(b), 1e-300))
+        return {"checker": "oracle on the isometric 2-variable image of the workload (bench.py: isometric_oracle_trace)",
+                "iterations_checked": len(seen), "evaluations_per_iteration_identical": same,
+                "max_rel_err_fx_xnorm_gnorm_step": worst,
+                "bar": "north_star: identical evaluation counts, 1e-10 relative (not widened)",
+                "bar_met": bool(same and worst <= 1e-10)}
+    except Exception as e:  # the checker must never break the measurement
+        return {"error": repr(e)}
+
+
+def nondegenerate_sharded_parity(R, D, dev, comm, world, rank, n=100_002, iters=40):
+    """A small NON-degenerate solve through the same sharded production path (TREE reductions, peer exchange when
+    world > 1): n = 100 002, x0 = (-1.2, 1) repeated scaled by linspace(0.9, 1.1) — every element different, uneven
+    shards — against the ORACLE (faithful, and compensated for the drift scale) on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    lo, hi = D.shard_range(n, rank, world)
+    x0 = np.empty(n)
+    x0[0::2], x0[1::2] = -1.2, 1.0
+    x0 *= np.linspace(0.9, 1.1, n)
+    x = torch.tensor(x0[lo:hi], dtype=torch.float64, device=dev)
+    b = R.lbfgs().with_max_iterations(iters)
+    if comm is not None:
+        b = b.with_shard(comm, n, lo)
+    spans = [D.shard_range(n, r, world) for r in range(world)]
+    width = max(h - l for l, h in spans)
+    trace = []
+
+    def on_progress(p):
+        xs = p.x
+        if world > 1:   # gather the iterate on every rank (same collective order everywhere: replicated control flow)
+            pad = torch.zeros(width, dtype=torch.float64, device=dev)
+            pad[: hi - lo] = xs
+            allx = torch.empty(world * width, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allx, pad)
+            if rank == 0:
+                xs = torch.cat([allx[r * width: r * width + (h - l)] for r, (l, h) in enumerate(spans)])
+        if rank == 0:
+            trace.append(dict(niter=p.niter, ncall=p.ncall, fx=p.fx, xnorm=p.xnorm, gnorm=p.gnorm, x=xs.cpu().numpy().copy()))
+        return False
+    obj = R.Rosenbrock()
+    rep = b.minimize(x, obj, on_progress)
+    obj.close()
+    if rank != 0:
+        return None
+    from oracle import oracle_lib as O
+    ref = O.minimize(O.default_param(max_iterations=iters), x0.copy(), O.Objective.builtin("rosenbrock"), record_x=True)
+    alt = O.minimize(O.default_param(max_iterations=iters, reduction_mode=1), x0.copy(), O.Objective.builtin("rosenbrock", 1),
+                     record_x=True)
+    same = len(trace) == len(ref["trace"]) and [t["ncall"] for t in trace] == [t["ncall"] for t in ref["trace"]]
+    ex = ef = drift = 0.0
+    for a, c, g in zip(ref["trace"], alt["trace"], trace):
+        if a["ncall"] != g["ncall"]:
+            break
+        sx = max(float(np.max(np.abs(a["x"]))), 1e-300)
+        ex = max(ex, float(np.max(np.abs(a["x"] - g["x"]))) / sx)
+        ef = max(ef, abs(a["fx"] - g["fx"]) / max(abs(a["fx"]), a["gnorm"] * a["xnorm"]))
+        drift = max(drift, float(np.max(np.abs(a["x"] - c["x"]))) / sx)
+    return {"checker": "oracle (faithful CPU restatement of the reference, sequential sums) on rank 0",
+            "n": n, "x0": "(-1.2, 1) repeated * linspace(0.9, 1.1)", "ranks": world, "iterations": len(trace),
+            "status": rep.status_name, "oracle_status": ref["status_name"],
+            "evaluations_per_iteration_identical": bool(same),
+            "max_rel_err_x": ex, "max_rel_err_fx": ef,
+            "drift_between_two_cpu_summation_orders_x": drift,
+            "bar": "north_star: identical status and evaluation counts, x and fx within 1e-10 over the first 50 iterations",
+            "bar_met": bool(same and rep.status_name == ref["status_name"] and ex <= 1e-10 and ef <= 1e-10)}
+
+
+def kernel_tables(prof, n_local, K, ms_total, peak):
+    launches, kbytes, kms = dict(prof["launches"]), dict(prof["bytes"]), dict(prof["ms"])
+    kbytes["evaluate"] = 2.0 * 8.0 * n_local * launches["evaluate"]     # Rosenbrock: 1R 1W per evaluation
+    moved = sum(kbytes.values())
+    evals = launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)
+    return launches, kbytes, kms, moved, evals
+
+
 def run_ours(args):
     import torch
     import rust_lbfgs_b200 as R
@@ -218,6 +394,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: rust_lbfgs_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpus = host_numa_cpus(local_rank)      # launching thread + pinned buffers on the GPU's own NUMA node
+    if cpus:
+        try:
+            os.sched_setaffinity(0, cpus)
+        except Exception:
+            cpus = None
     comm = None
     if world > 1:
         import torch.distributed as dist
@@ -232,107 +414,56 @@ def run_ours(args):
 
     n_local = int(args.n)
     n_global = n_local * world
-    goff = rank * n_local
     K, W, m = args.steps, args.warmup, args.m
-
-    def make_builder():
-        b = R.lbfgs().with_m(m).with_fused_trial(not args.unfused_trial)
-        if comm is not None:
-            b = b.with_shard(comm, n_global, goff)
-        return b
-
-    def fill_x0(t):
-        t[0::2] = -1.2
-        t[1::2] = 1.0
-
-    obj = R.Rosenbrock()
+    fused = False if args.unfused_trial else ("trial" if args.fused_trial_only else "probe")
+    peak, peak_src = load_peaks()
 
     # ---- device-resident run: `value`, roofline ------------------------------------------------
-    x = torch.empty(n_local, dtype=torch.float64, device=dev)
-    fill_x0(x)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
         sampler.start()                     # nvidia-smi needs ~0.5 s to produce its first sample: start it early
-    state = make_builder().build(x, obj)
-    state.propagate()                       # propagate #1 is the reference's no-op (src/lbfgs.rs:507-510)
-    for _ in range(W):
-        state.propagate()
-    # CUDA events around the dominant kernel only inside the timed region (events around every launch cost
-    # ~2 % at n = 1e8); the other kernels are timed in a separate pass after it
     DOM = "backward"
-    state.profile_enable(True, kinds=[DOM])
-    state.profile_reset()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
-    wall_begin = time.time()
-    ev0.record()
-    ncalls, seen = [], []
-    for _ in range(K):
-        p = state.propagate()
-        ncalls.append(p.ncall)
-        seen.append((p.niter, p.ncall, p.fx, p.xnorm, p.gnorm, p.step))
-    ev1.record()
-    torch.cuda.synchronize()
-    wall_end = time.time()
-    barrier()
-    clocks = sampler.stop(wall_begin, wall_end) if rank == 0 else None
-    ms_total = D.max_over_ranks(ev0.elapsed_time(ev1))
-    prof = state.profile()
-    final = state.report()
-    # per-kernel profile pass (NOT part of `value`): a few more iterations with events around every launch
-    state.profile_enable(True)
-    state.profile_reset()
     P = max(3, min(10, K))
-    for _ in range(P):
-        state.propagate()
-    prof_all = state.profile()
-    state.finish()
-    state.close()
-
-    launches, kbytes, kms = prof["launches"], prof["bytes"], prof["ms"]
+    r = timed_iterations(R, D, dev, comm, world, n_local, m, K, W, fused, barrier, sampler, DOM, profile_pass=P)
+    ms_total, clocks, seen, final = r["ms_total"], r["clocks"], r["seen"], r["final"]
+    launches, kbytes, kms, moved, evals = kernel_tables(r["prof"], n_local, K, ms_total, peak)
     gpu_launches = int(sum(launches.values()))
-    it_per_s = K / (ms_total / 1e3)
-    value = it_per_s * n_global / N_REF
+    value = K / (ms_total / 1e3) * n_global / N_REF
 
-    peak, peak_src = load_peaks()
-    dom = DOM
-    dom_gbs = (kbytes[dom] / 1e9) / (kms[dom] / 1e3) if kms[dom] > 0 else None
+    dom_gbs = (kbytes[DOM] / 1e9) / (kms[DOM] / 1e3) if kms[DOM] > 0 else None
     traffic = load_traffic()
     roofline = {
-        "bound": "hbm", "kernel": f"two_loop_{dom}_step (k_{dom})", "achieved": dom_gbs, "peak": peak,
+        "bound": "hbm", "kernel": f"two_loop_{DOM}_step (k_{DOM})", "achieved": dom_gbs, "peak": peak,
         "unit": "GB/s", "frac": (dom_gbs / peak) if dom_gbs else None,
         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
         "peak_source": peak_src,
-        "launches": int(launches[dom]), "avg_launch_ms": kms[dom] / max(1, launches[dom]),
-        "algorithmic_bytes_per_launch": kbytes[dom] / max(1, launches[dom]),
+        "launches": int(launches[DOM]), "avg_launch_ms": kms[DOM] / max(1, launches[DOM]),
+        "algorithmic_bytes_per_launch": kbytes[DOM] / max(1, launches[DOM]),
     }
-    kbytes["evaluate"] = 2.0 * 8.0 * n_local * launches["evaluate"]     # Rosenbrock: 1R 1W per evaluation
     surv_bytes = algorithmic_bytes_survey(n_local, launches, kbytes)
-    moved = sum(kbytes.values())
+    pa = r["prof_all"]
     iteration = {
         # bytes the launched kernels must move (DESIGN.md §3 per-kernel passes x 8n) / wall time of the K steps
-        "algorithmic_GBps": moved / 1e9 / (ms_total / 1e3),
-        "frac_of_peak": moved / 1e9 / (ms_total / 1e3) / peak,
-        "algorithmic_bytes_per_iteration": moved / max(1, K),
-        # SURVEY.md §8(d)'s formula prices a trial at 8V (K1 + evaluate + K2); the fused trial moves 4V, so this
+        "algorithmic_GBps": moved * world / 1e9 / (ms_total / 1e3),
+        "algorithmic_GBps_per_gpu": moved / 1e9 / (ms_total / 1e3),
+        "frac_of_peak_per_gpu": moved / 1e9 / (ms_total / 1e3) / peak,
+        "algorithmic_bytes_per_iteration_per_gpu": moved / max(1, K),
+        # SURVEY.md §8(d)'s formula prices a trial at 8V (K1 + evaluate + K2); probes move 2V, so this
         # "unfused-equivalent" rate can exceed what the HBM actually carried — reported for comparison only
-        "survey_formula_equivalent_GBps": surv_bytes / 1e9 / (ms_total / 1e3),
+        "survey_formula_equivalent_GBps_per_gpu": surv_bytes / 1e9 / (ms_total / 1e3),
         "line_search_trials": ("probe + commit" if launches.get("probe", 0) > 0 else
                                "fused trial" if launches.get("trial_eval", 0) > 0 else "unfused (K1 + evaluate + K2)"),
-        "evaluations_per_iteration": (launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)) / max(1, K),
+        "evaluations_per_iteration": evals / max(1, K),
         "kernel_ms_timed_region": {k: round(v, 3) for k, v in kms.items() if v > 0},
         "profile_pass": {
             "note": f"{P} extra iterations after the timed region with CUDA events around every launch",
-            "kernel_ms": {k: round(v, 3) for k, v in prof_all["ms"].items() if v > 0},
-            "kernel_GBps": {k: round(prof_all["bytes"][k] / 1e9 / (prof_all["ms"][k] / 1e3), 1) for k in prof_all["ms"]
-                            if prof_all["ms"][k] > 0 and prof_all["bytes"][k] > 0},
+            "kernel_ms": {k: round(v, 3) for k, v in pa["ms"].items() if v > 0},
+            "kernel_GBps": {k: round(pa["bytes"][k] / 1e9 / (pa["ms"][k] / 1e3), 1) for k in pa["ms"]
+                            if pa["ms"][k] > 0 and pa["bytes"][k] > 0},
         },
-        "host_syncs": prof["host_syncs"], "allreduces": prof["allreduces"],
-        "allreduce_transport": comm.transport if comm is not None else None,
+        "host_syncs": r["prof"]["host_syncs"], "allreduces": r["prof"]["allreduces"],
+        "allreduce_transport": r["transport"],
     }
-    del x
-    torch.cuda.empty_cache()
 
     # ---- end to end through the public API with HOST buffers: `e2e` ---------------------------------
     # The reference-shaped call: x is a HOST slice (src/lbfgs.rs:399), passed to the C ABI's host-buffer entry.
@@ -341,8 +472,12 @@ def run_ours(args):
     # happen once per solve, so bytes/step are 8n/(W+K) each way (+ the few scalars read back per iteration).
     iters_e2e = W + K
     xh = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
-    fill_x0(xh)
-    builder = make_builder().with_max_iterations(iters_e2e + 1)
+    xh[0::2] = -1.2
+    xh[1::2] = 1.0
+    builder = R.lbfgs().with_m(m).with_fused_trial(fused).with_max_iterations(iters_e2e + 1)
+    if comm is not None:
+        builder = builder.with_shard(comm, n_global, rank * n_local)
+    obj = R.Rosenbrock()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -356,40 +491,63 @@ def run_ours(args):
         "h2d_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters),
         "d2h_bytes_per_step": 8.0 * n_local * world / max(1, e2e_iters) + 64.0 * 3,
         "iterations": e2e_iters, "seconds": e2e_s, "evaluations": rep.neval,
+        "host_buffer": "pinned, allocated on the GPU's NUMA node" if cpus else "pinned",
         "note": "one lbfgsb200_minimize_host_ex() call on a pinned HOST buffer: H2D of x0, solver creation, build, "
                 "W+K iterations, D2H of x, teardown",
     }
     del xh
+    obj.close()
 
-    # ---- the timed trajectory against the reference algorithm (checker only; rank 0) -------------------------
+    # ---- parity of what was just timed (checker only; rank 0) -----------------------------------------------
     parity = None
-    if rank == 0 and not args.no_cpu_baseline and n_global % 2 == 0:
+    if not args.no_cpu_baseline:
+        parity = {}
+        if rank == 0 and n_global % 2 == 0:
+            parity["timed_trajectory"] = isometric_parity(seen, n_global, m, 1 + W + K)
         try:
-            ref = {t["niter"]: t for t in isometric_oracle_trace(n_global, m, 1 + W + K)}
-            worst = 0.0
-            same = True
-            for (it, nc, fx, xn, gn, stp) in seen:
-                t = ref.get(it)
-                if t is None or t["ncall"] != nc:
-                    same = False
-                    break
-                for a, b in ((fx, t["fx"]), (xn, t["xnorm"]), (gn, t["gnorm"]), (stp, t["step"])):
-                    worst = max(worst, abs(a - b) / max(abs(b), 1e-300))
-            parity = {"checker": "oracle on the isometric 2-variable image of the workload (bench.py: isometric_oracle_trace)",
-                      "iterations_checked": len(seen), "evaluations_per_iteration_identical": same,
-                      "max_rel_err_fx_xnorm_gnorm_step": worst}
-        except Exception as e:  # the checker must never break the measurement
-            parity = {"error": repr(e)}
+            nd = nondegenerate_sharded_parity(R, D, dev, comm, world, rank)
+        except Exception as e:
+            nd = {"error": repr(e)}
+        if rank == 0:
+            parity["nondegenerate_sharded_solve"] = nd
 
-    # ---- the reference's CPU path on this host (rank 0, N=1 only) -------------------------------------
+    # ---- BASELINE configs[4]: Rosenbrock n = 2^31, m = 20 sharded over 8 GPUs = 2^28 elements per GPU -----------
+    # Run at every N (weak scaling at 2^28 per GPU), so the driver's own N = 1, 2, 4, 8 set yields north_star's
+    # "sharded n = 2^31, m = 20 scales >= 6x from 1 to 8 GPUs" from its per-N lines.
+    config5 = None
+    if not args.no_config5:
+        n5, m5, K5, W5 = 1 << 28, 20, max(10, min(K, 20)), 3
+        R.lib().lbfgsb200_trim_pool(local_rank)    # hand the n = 1e8 arenas back before asking for 92 GiB
+        free_b, _ = torch.cuda.mem_get_info()
+        if free_b > (2 * m5 + 7) * 8 * n5 * 1.03:
+            r5 = timed_iterations(R, D, dev, comm, world, n5, m5, K5, W5, fused, barrier, None, DOM)
+            l5, kb5, km5, moved5, ev5 = kernel_tables(r5["prof"], n5, K5, r5["ms_total"], peak)
+            config5 = {
+                "workload": "Rosenbrock n=2^28 f64 per GPU (n=2^31 on 8 GPUs), m=20, MoreThuente (BASELINE.json configs[4])",
+                "n_per_gpu": n5, "n_global": n5 * world, "m": m5, "steps": K5, "warmup": W5, "scaling": "weak",
+                "ms_per_step": r5["ms_total"] / K5,
+                # element-iterations/s in units of 2^28 elements: plain iterations/s on one GPU; the 1 -> N factor is
+                # this value at N over this value at 1
+                "value": K5 / (r5["ms_total"] / 1e3) * world, "unit": "it/s x n_global/2^28",
+                "algorithmic_GBps": moved5 * world / 1e9 / (r5["ms_total"] / 1e3),
+                "algorithmic_GBps_per_gpu": moved5 / 1e9 / (r5["ms_total"] / 1e3),
+                "frac_of_peak_per_gpu": moved5 / 1e9 / (r5["ms_total"] / 1e3) / peak,
+                "evaluations_per_iteration": ev5 / K5,
+                "k_backward_GBps": (kb5[DOM] / 1e9) / (km5[DOM] / 1e3) if km5[DOM] > 0 else None,
+                "parity": isometric_parity(r5["seen"], n5 * world, m5, 1 + W5 + K5) if (rank == 0 and not args.no_cpu_baseline) else None,
+            }
+        else:
+            config5 = {"skipped": f"needs {(2 * m5 + 7) * 8 * n5 / 2**30:.0f} GiB of free HBM, {free_b / 2**30:.0f} GiB free"}
+
+    # ---- the reference's CPU path on this host (rank 0, N=1 only), on the quoted size ---------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_sample = int(args.cpu_n)
-        rate, dt, done = cpu_oracle_rate(n_sample, min(W, 2), args.cpu_steps, m=m, budget_s=25.0)
+        rate, dt, done = cpu_oracle_rate(n_sample, 1, args.cpu_steps, m=m, budget_s=args.cpu_budget)
         if rate:
             cpu = {"value": rate * n_sample / N_REF, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"oracle (C++ port of the reference, 1 thread) Rosenbrock n={n_sample}, m={m}, "
-                             f"{done} iterations after {min(W, 2)} warm-up in {dt:.1f} s; it/s scaled by n_sample/1e8",
+                   "sample": f"oracle (C++ port of the reference, 1 thread) Rosenbrock n={n_sample}, m={m}: iterations 2.."
+                             f"{1 + done} in {dt:.1f} s" + ("" if n_sample == N_REF else "; it/s scaled by n_sample/1e8"),
                    "host_cores_available": os.cpu_count()}
 
     if rank == 0:
@@ -397,13 +555,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (n_local == N_REF and m == 6) else
-                       f"Rosenbrock n={n_local} f64 per GPU, m={m}, MoreThuente, device-resident evaluate",
-                       "n_per_gpu": n_local, "n_global": n_global, "m": m, "linesearch": "MoreThuente",
-                       "l2_policy": "inputs larger than L2 (19 vectors x 0.8 GB vs 126 MB)",
-                       "ncall_per_iteration": ncalls, "final_fx": final.fx, "final_gnorm": final.gnorm},
+            "config": workload_config(n_local, n_global, m),
+            "run": {"ncall_per_iteration": [s[1] for s in seen], "final_fx": final.fx, "final_gnorm": final.gnorm,
+                    "host_numa_cpus": len(cpus) if cpus else None},
             "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
-            "gpu_launches": gpu_launches, "clocks": clocks,
+            "config5": config5, "gpu_launches": gpu_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -421,12 +577,17 @@ def main():
     # (--elems / --history: torchrun's own parser chokes on "--n" / "--m" as ambiguous abbreviations)
     ap.add_argument("--n", "--elems", dest="n", type=float, default=1e8, help="elements per GPU")
     ap.add_argument("--m", "--history", dest="m", type=int, default=6)
-    ap.add_argument("--ref-n", type=float, default=5e6, help="--impl reference: sample size")
-    ap.add_argument("--cpu-n", type=float, default=2e7, help="cpu_baseline sample size")
-    ap.add_argument("--cpu-steps", type=int, default=8)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-n", type=float, default=1e8, help="--impl reference: elements (the quoted configuration: 1e8)")
+    ap.add_argument("--ref-budget", type=float, default=420.0, help="--impl reference: seconds of timed iterations at most")
+    ap.add_argument("--cpu-n", type=float, default=1e8, help="cpu_baseline: elements")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="cpu_baseline: seconds of timed iterations at most")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline and the oracle-side parity checks")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 2^28-per-GPU, m=20 block")
     ap.add_argument("--unfused-trial", action="store_true",
-                    help="line-search trials as K1 + evaluate + K2 (three passes) instead of the fused one-pass trial")
+                    help="line-search trials as K1 + evaluate + K2 (three passes)")
+    ap.add_argument("--fused-trial-only", action="store_true",
+                    help="the one-pass trial that writes x and g (round 1's path) instead of probe + commit")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: W >= 3

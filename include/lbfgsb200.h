@@ -420,9 +420,10 @@ int  lbfgsb200_device_free(void *dev);
 int  lbfgsb200_copy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
 int  lbfgsb200_copy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
 int  lbfgsb200_stream_synchronize(void *stream);
-/* Solver arenas come from the device's default CUDA memory pool and stay cached there after
- * lbfgsb200_destroy, so repeated solves do not pay the driver's map/unmap of ~(2m+5) n-vectors each time.
- * This hands the cached pages back to the driver (e.g. before another library needs the HBM). */
+/* Solver arenas come from a private CUDA memory pool per device (the device's default pool is left alone) and
+ * stay cached there after lbfgsb200_destroy, so repeated solves do not pay the driver's map/unmap of ~(2m+5)
+ * n-vectors each time.  This hands the cached pages back to the driver (e.g. before another library needs the
+ * HBM).  LBFGSB200_POOL=0 disables the pool. */
 int  lbfgsb200_trim_pool(int device);
 int  lbfgsb200_abi_version(void);
 

@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,6 +29,7 @@ namespace {
 typedef std::vector<double> Vec;
 
 int g_mode = 0;  // reduction mode of the solve in flight (the oracle is single-threaded)
+int g_ls_variant = 0;  // experiment switch, see line_search_morethuente
 
 // ----- sums ---------------------------------------------------------------------------
 struct Acc {
@@ -375,7 +377,10 @@ LsErr line_search_morethuente(Problem &prb, double &stp, const LineSearch &param
         if (stp == param.max_step && f <= ftest1 && dg <= dgtest) return LS_ERR_MAX_STEP;    // :305-308
         if (stp == param.min_step && (ftest1 < f || dgtest <= dg)) return LS_ERR_MIN_STEP;   // :310-313
 
-        if (std::fabs(dg) <= param.gtol * -dginit) {  // :315-317 (curvature alone)
+        // ORACLE_LS_VARIANT=1 (an experiment, never the default): skip the curvature-only exit so that only the
+        // sufficient-decrease + curvature branch below can end the search — the C liblbfgs condition that :315-317
+        // shadows.  Used by scripts/explain_iteration_counts.py to explain tests/simple.rs:33-35,48-50.
+        if (g_ls_variant != 1 && std::fabs(dg) <= param.gtol * -dginit) {  // :315-317 (curvature alone)
             ncall = count;
             return LS_OK;
         } else if (f <= ftest1 && std::fabs(dg) <= param.gtol * -dginit) {  // :318-320 (unreachable)
@@ -674,6 +679,10 @@ int oracle_minimize(const oracle_param_t *param, double *x, int64_t n, oracle_ev
         return st;
     };
     g_mode = (int)param->reduction_mode;
+    {
+        const char *v = getenv("ORACLE_LS_VARIANT");
+        g_ls_variant = (v && v[0] == '1') ? 1 : 0;
+    }
 
     Owl owl;
     owl.on = param->orthantwise != 0;

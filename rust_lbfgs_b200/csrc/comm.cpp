@@ -40,6 +40,7 @@ struct Nccl {
     int (*GetUniqueId)(ncclUniqueId *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*CommAbort)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -62,6 +63,7 @@ Nccl &nccl() {
         n.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(n.handle, "ncclGetUniqueId");
         n.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(n.handle, "ncclCommInitRank");
         n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommDestroy");
+        n.CommAbort = (int (*)(ncclComm_t))dlsym(n.handle, "ncclCommAbort");
         n.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
         n.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclAllGather");
         n.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.handle, "ncclBroadcast");
@@ -81,7 +83,8 @@ struct Comm {
     // peer mailboxes (transport 1)
     PeerCtx peer{};                    // nranks == 0: not available, use NCCL
     unsigned long long seq = 0;        // exchange counter, advanced identically on every rank
-    double *mailbox = nullptr;         // this rank's ring: kMailRing x nranks entries of kMailStride doubles
+    double *mailbox = nullptr;         // this rank's ring: kMailRing x nranks entries of kMailStride doubles, then the fault word
+    bool aborted = false;              // ncclCommAbort was called (setup could not even stage its handshake)
     double **mail_table = nullptr;     // device array of every rank's mailbox pointer (as mapped here)
     void *opened[kMaxPeers] = {};
 };
@@ -90,6 +93,13 @@ int comm_rank(const Comm *c) { return c ? c->rank : 0; }
 int comm_size(const Comm *c) { return c ? c->nranks : 1; }
 const PeerCtx *comm_peer(const Comm *c) { return (c && c->peer.nranks > 1) ? &c->peer : nullptr; }
 unsigned long long *comm_peer_seq(Comm *c) { return c ? &c->seq : nullptr; }
+// 1 if a reducing kernel gave up waiting for a peer's mailbox entry (the sums it returned are NaN)
+int comm_peer_fault(const Comm *c) {
+    if (!c || !c->peer.fault) return 0;
+    unsigned int v = 0;
+    if (cudaMemcpy(&v, c->peer.fault, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return v != 0;
+}
 
 namespace {
 // Maps every rank's mailbox into this process.  Collective; returns false (on every rank) if any rank failed.
@@ -97,17 +107,26 @@ bool setup_peer_mailboxes(Comm *c) {
     Nccl &n = nccl();
     const char *env = getenv("LBFGSB200_PEER_REDUCE");
     bool ok = !(env && env[0] == '0') && n.AllGather && c->nranks <= kMaxPeers;
-    const size_t bytes = sizeof(double) * kMailRing * (size_t)c->nranks * kMailStride;
+    const size_t ring_bytes = sizeof(double) * kMailRing * (size_t)c->nranks * kMailStride;
+    const size_t bytes = ring_bytes + 128;   // + the fault word
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
-    if (ok) ok = cudaMalloc((void **)&c->mailbox, bytes) == cudaSuccess;
-    if (ok) ok = cudaMemset(c->mailbox, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
-    if (ok) ok = cudaIpcGetMemHandle(&mine, c->mailbox) == cudaSuccess;
-    // all-gather the handles (+ one status byte per rank) through NCCL
+    // The staging buffer of the handshake comes first: every later failure is reported THROUGH the collectives
+    // below (status byte 0), so no rank is left waiting in them.  If not even these few hundred bytes can be
+    // allocated the communicator is aborted, which makes the peers' collectives fail instead of hang.
     const size_t rec = sizeof(cudaIpcMemHandle_t) + 16;
     unsigned char *dev = nullptr;
     std::vector<unsigned char> host(rec * c->nranks, 0);
-    if (cudaMalloc((void **)&dev, rec * c->nranks) != cudaSuccess) return false;  // cannot even talk: caller falls back
+    if (cudaMalloc((void **)&dev, rec * c->nranks) != cudaSuccess) {
+        cudaGetLastError();
+        if (n.CommAbort) { n.CommAbort(c->comm); c->comm = nullptr; c->aborted = true; }
+        return false;
+    }
+    if (ok) ok = cudaMalloc((void **)&c->mailbox, bytes) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->mailbox, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->mailbox) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    // all-gather the handles (+ one status byte per rank) through NCCL
     memcpy(&host[rec * c->rank], &mine, sizeof(mine));
     host[rec * c->rank + sizeof(mine)] = ok ? 1 : 0;
     cudaMemcpy(dev, host.data(), rec * c->nranks, cudaMemcpyHostToDevice);
@@ -154,6 +173,7 @@ bool setup_peer_mailboxes(Comm *c) {
     c->peer.mail_table = c->mail_table;
     c->peer.seq = 0;
     c->peer.extra[0] = c->peer.extra[1] = nullptr;
+    c->peer.fault = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(c->mailbox) + ring_bytes);
     return true;
 }
 }  // namespace
@@ -161,7 +181,7 @@ bool setup_peer_mailboxes(Comm *c) {
 int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream) {
     if (!c || c->nranks == 1) return 0;
     Nccl &n = nccl();
-    if (!n.ok) return LBFGSB200_ERR_NCCL;
+    if (!n.ok || !c->comm) return LBFGSB200_ERR_NCCL;
     int rc = n.AllReduce(buf_dev, buf_dev, (size_t)count, ncclFloat64, ncclSum, c->comm, stream);
     return rc == ncclSuccess ? 0 : LBFGSB200_ERR_NCCL;
 }
@@ -171,7 +191,7 @@ int comm_allreduce_sum(Comm *c, double *buf_dev, int count, cudaStream_t stream)
 int comm_allgatherv(Comm *c, const double *send, double *recv_all, const int64_t *offsets, cudaStream_t stream) {
     if (!c || c->nranks == 1) return 0;
     Nccl &n = nccl();
-    if (!n.ok || !n.Broadcast || !n.GroupStart || !n.GroupEnd) return LBFGSB200_ERR_NCCL;
+    if (!n.ok || !c->comm || !n.Broadcast || !n.GroupStart || !n.GroupEnd) return LBFGSB200_ERR_NCCL;
     if (n.GroupStart() != ncclSuccess) return LBFGSB200_ERR_NCCL;
     int bad = 0;
     for (int r = 0; r < c->nranks; ++r) {

@@ -437,17 +437,21 @@ int launch_glm_fused(Objective *o, const double *w, double *g, cudaStream_t stre
     if (stages > kGlmMaxStages) stages = kGlmMaxStages;
     if (stages < 2) return LBFGSB200_ERR_UNSUPPORTED;
     const size_t smem = (size_t)stages * stage_stride;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_glm_fused<KP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return LBFGSB200_ERR_CUDA;
-        attr_set = true;
+    static bool attr_set[64] = {};   // function attributes are per device: one opt-in per (instantiation, device)
+    const int di = o->dev.device;
+    if (di < 0 || di >= 64 || !attr_set[di]) {
+        if (cudaFuncSetAttribute(k_glm_fused<KP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return LBFGSB200_ERR_UNSUPPORTED;   // the caller falls back to the two-pass kernels
+        }
+        if (di >= 0 && di < 64) attr_set[di] = true;
     }
     const int64_t ngroups = (o->nrow + R - 1) / R;
     int grid = o->dev.sm_count;
     if ((int64_t)grid > ngroups) grid = (int)ngroups;
     k_glm_fused<KP, R><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind, stages,
                                                           stage_stride, o->ws, fx);
+    if (cudaGetLastError() != cudaSuccess) return LBFGSB200_ERR_UNSUPPORTED;   // launch refused: two-pass kernels instead
     const unsigned cb = (unsigned)((o->ncol + kThreads - 1) / kThreads);
     k_glm_grad_final<<<cb, kThreads, 0, stream>>>(o->gfused, g, o->ncol, grid);
     return 0;

@@ -51,6 +51,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#ifndef LB_PEER_TIMEOUT_MS
+#define LB_PEER_TIMEOUT_MS 20000
+#endif
+constexpr unsigned long long kPeerTimeoutNs = (unsigned long long)LB_PEER_TIMEOUT_MS * 1000000ull;
 // In/out: tab[kMaxPeers][0..nv) in shared memory (written by lane 0 before the call, read by it afterwards).
 __device__ __forceinline__ void peer_allreduce(const PeerCtx &pc, int nv, double (*tab)[kMailVals]) {
     const int lane = threadIdx.x & 31;
@@ -70,8 +74,9 @@ __device__ __forceinline__ void peer_allreduce(const PeerCtx &pc, int nv, double
         const unsigned long long t0 = globaltimer_ns();
         bool ok = true;
         while (*reinterpret_cast<volatile unsigned long long *>(src) != seq) {
-            if (globaltimer_ns() - t0 > 20000000000ull) { ok = false; break; }  // 20 s: a peer died
+            if (globaltimer_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }  // a peer died (or never launched)
         }
+        if (!ok && pc.fault) atomicExch(pc.fault, 1u);   // the host turns this into LBFGSB200_ERR_NCCL (Solver::fetch)
         __threadfence_system();
         for (int a = 0; a < nv; ++a) tab[lane][a] = ok ? src[1 + a] : __longlong_as_double(0x7ff8000000000000ll);
     }

@@ -111,34 +111,43 @@ void scratch_release(const Scratch &s) {
 }
 }  // namespace
 
-// The arena (2m + 4..5 n-vectors: 12.8 GB at n = 1e8, m = 6) comes from the device's default CUDA memory pool
-// with the release threshold lifted, so a process that solves repeatedly pays the driver's map/unmap of
-// those pages once (measured on B200: cudaMalloc + cudaFree of the arena cost 30 ms .. 1.3 s per solve,
-// against ~9 ms per L-BFGS iteration).  lbfgsb200_trim_pool() hands the cached pages back.
-// LBFGSB200_POOL=0 falls back to cudaMalloc / cudaFree.
-static bool use_pool(int device) {
-    static int cached[64];  // 0 = unknown, 1 = pool, 2 = plain
-    if (device < 0 || device >= 64) return false;
-    if (cached[device] == 0) {
+// The arena (2m + 4..5 n-vectors: 12.8 GB at n = 1e8, m = 6) comes from a PRIVATE CUDA memory pool per device whose
+// release threshold is lifted, so a process that solves repeatedly pays the driver's map/unmap of those pages
+// once (measured on B200: cudaMalloc + cudaFree of the arena cost 30 ms .. 1.3 s per solve, against ~8 ms per
+// L-BFGS iteration).  The device's default pool — which other libraries in the process may use — is left alone.
+// lbfgsb200_trim_pool() hands the cached pages back.  LBFGSB200_POOL=0 falls back to cudaMalloc / cudaFree.
+namespace {
+std::mutex g_pool_mu;
+cudaMemPool_t g_pool[64];
+int g_pool_state[64];  // 0 = unknown, 1 = pool, 2 = plain
+}  // namespace
+static cudaMemPool_t arena_pool(int device) {
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (g_pool_state[device] == 0) {
         int ok = 0;
         cudaMemPool_t pool = nullptr;
         if (env_int("LBFGSB200_POOL", 1) != 0 &&
-            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && ok &&
-            cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && ok) {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
             uint64_t keep = UINT64_MAX;
-            ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+            ok = cudaMemPoolCreate(&pool, &props) == cudaSuccess &&
+                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
         } else {
             ok = 0;
         }
         cudaGetLastError();
-        cached[device] = ok ? 1 : 2;
+        g_pool[device] = ok ? pool : nullptr;
+        g_pool_state[device] = ok ? 1 : 2;
     }
-    return cached[device] == 1;
+    return g_pool_state[device] == 1 ? g_pool[device] : nullptr;
 }
 
 int trim_pool(int device) {
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     if (cudaDeviceSynchronize() != cudaSuccess) return LBFGSB200_ERR_CUDA;
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
@@ -151,6 +160,12 @@ int trim_pool(int device) {
             }
         }
     }
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (device >= 0 && device < 64 && g_pool_state[device] == 1) pool = g_pool[device];
+    }
+    if (!pool) return 0;   // nothing was ever pooled on this device
     return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
@@ -247,8 +262,9 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     const int64_t vec_bytes = round_up(n_ * (int64_t)sizeof(double), kAlign);
     const int64_t nvec = 4 + (owl_ ? 1 : 0) + 2 * m_ + 1;
     const int64_t wp_bytes = owl_ ? round_up(n_, kAlign) : 0;
-    arena_pooled_ = use_pool(device);
-    if (arena_pooled_) e = cudaMallocAsync(&arena_, (size_t)(nvec * vec_bytes + wp_bytes), stream_);
+    cudaMemPool_t pool = arena_pool(device);
+    arena_pooled_ = pool != nullptr;
+    if (arena_pooled_) e = cudaMallocFromPoolAsync(&arena_, (size_t)(nvec * vec_bytes + wp_bytes), pool, stream_);
     else e = cudaMalloc(&arena_, (size_t)(nvec * vec_bytes + wp_bytes));
     if (e != cudaSuccess) { arena_ = nullptr; return cuda_fail(e, "cudaMalloc(arena)"); }
     tm.lap("create: arena");
@@ -289,6 +305,8 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     if (force == 1) streaming_ = true;
     memset(&prof_, 0, sizeof(prof_));
     graphs_enabled_ = env_int("LBFGSB200_GRAPHS", 1) != 0;
+    small_enabled_ = env_int("LBFGSB200_SMALL", 1) != 0;
+    ring_stride_ = vec_bytes / (int64_t)sizeof(double);
     return 0;
 }
 
@@ -366,7 +384,18 @@ int Solver::fetch(int s, int count, double *host, bool ours) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
     if (timing_) prof_resolve();
     for (int i = 0; i < count; ++i) host[i] = scal_host_[i];
-    return 0;
+    return check_peers(host, count);
+}
+
+// A reducing kernel that waited in vain for a peer's mailbox entry returns NaN sums and raises the communicator's
+// fault word; NaN alone is a legitimate value (the objective may produce it), so the word decides.  Only looked at
+// when something is NaN: no cost on the normal path.
+int Solver::check_peers(const double *h, int count) {
+    if (!comm_ || comm_size(comm_) == 1 || !comm_peer(comm_)) return 0;
+    bool nan = false;
+    for (int i = 0; i < count; ++i) nan = nan || std::isnan(h[i]);
+    if (!nan || !comm_peer_fault(comm_)) return 0;
+    return fail(LBFGSB200_ERR_NCCL, "a peer rank did not post its partial sums in time (dead or out of step)");
 }
 
 // Two slots (already summed over the ranks) with one synchronisation.
@@ -380,7 +409,8 @@ int Solver::fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2) {
     if (timing_) prof_resolve();
     for (int i = 0; i < c1; ++i) h1[i] = scal_host_[i];
     for (int i = 0; i < c2; ++i) h2[i] = scal_host_[kMaxAcc + i];
-    return 0;
+    const int rc = check_peers(h1, c1);
+    return rc != 0 ? rc : check_peers(h2, c2);
 }
 
 // Problem::evaluate (src/core.rs:119-132) followed by the reductions the driver needs at this
@@ -629,6 +659,35 @@ int Solver::enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, i
     return 0;
 }
 
+// The launch-bound regime: all 2 * bound trips in one cluster-persistent kernel (small.cu).  One GPU, tree
+// reductions; anything it cannot take (or a refused cluster launch) goes to the multi-kernel chain.
+bool Solver::small_eligible() const {
+    if (!small_enabled_ || sequential_ || m_ > 64) return false;
+    if (comm_ && comm_size(comm_) > 1) return false;
+    return n_ <= two_loop_small_max_n();
+}
+
+int Solver::two_loop_small(const Launch &L, int64_t bound, int *so_last) {
+    const double vbytes = 8.0 * (double)n_;
+    prof_begin(LBFGSB200_K_UPDATE_SMALL);
+    const cudaError_t e = launch_two_loop_small(L, dev_.device, n_, (int)m_, (int)bound, (int)end_, d_, owl_ ? pg_ : gbuf_[cur_g_],
+                                                S_[0], ring_stride_, ys_dev_, slot(SLOT_HIST), slot(SLOT_LOOP_A), owl_,
+                                                owl_start_, owl_end_, goff_);
+    if (e != cudaSuccess) {   // refused (cluster shape / shared memory): never try again, use the chain
+        cudaGetLastError();
+        if (timing_ && ((timing_mask_ >> LBFGSB200_K_UPDATE_SMALL) & 1u)) {   // undo prof_begin's pending record
+            event_pool_.push_back(pending_.back().a);
+            event_pool_.push_back(pending_.back().b);
+            pending_.pop_back();
+        }
+        small_enabled_ = false;
+        return enqueue_two_loop(L, nullptr, bound, so_last);
+    }
+    prof_end(LBFGSB200_K_UPDATE_SMALL, (8.0 * (double)bound - 1.0) * vbytes);
+    *so_last = SLOT_LOOP_A;
+    return 0;
+}
+
 // CUDA-graph replay of enqueue_two_loop for the launch-bound regime.  The kernel arguments of the chain depend only
 // on the ring position (which s/y slots), the x/g buffer parity and — fixed for a solver — the option set, so
 // after the history ring is full there are at most 2m distinct chains; each is captured once and then replayed
@@ -768,7 +827,8 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     int rc = 0;
     rc = enqueue_history(L, xp, gp, stp_eval);
     if (rc != 0) return rc;
-    if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
+    if (small_eligible()) rc = two_loop_small(L, bound, &so_last);
+    else if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
     else rc = enqueue_two_loop(L, gp, bound, &so_last);
     if (rc != 0) return rc;
     end_ = (end_ + 1) % m_;

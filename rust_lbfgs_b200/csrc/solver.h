@@ -29,6 +29,7 @@ int comm_allgatherv(Comm *c, const double *send, double *recv_all, const int64_t
 // peer-mailbox transport (nullptr: not available, the solver calls comm_allreduce_sum instead)
 const PeerCtx *comm_peer(const Comm *c);
 unsigned long long *comm_peer_seq(Comm *c);
+int comm_peer_fault(const Comm *c);
 
 // Launch configuration for a device (SM count, L2 size, env overrides); shared by the solver,
 // the stand-alone primitives and the built-in objectives.
@@ -96,6 +97,7 @@ class Solver {
     void post_eval_flag(int erc);
     int fetch(int s, int count, double *host, bool ours = true);   // allreduce + D2H + sync of a slot
     int fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2);  // two reduced slots, one sync
+    int check_peers(const double *h, int count);                   // NaN sums + the communicator's fault word => ERR_NCCL
     // ours = the slot was produced by one of our reducing kernels (already exchanged inside it with peer mailboxes)
     int reduce_across_ranks(int s, int count, bool ours = true);
     void fill_progress(lbfgsb200_progress_t *out, double step_value) const;
@@ -104,6 +106,8 @@ class Solver {
     int enqueue_history(const Launch &L, const double *xp, const double *gp, double step_eval);
     // (+ damping) + two-loop of one iteration, enqueued on L.stream; *so_last = slot of the final dots
     int enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, int *so_last);
+    bool small_eligible() const;   // the cluster-persistent two-loop kernel (small.cu) applies
+    int two_loop_small(const Launch &L, int64_t bound, int *so_last);
     bool graph_eligible(int64_t bound) const;
     int two_loop_graphed(const Launch &L, const double *gp, int64_t bound, int *so_last);
     void drop_graphs();
@@ -128,7 +132,7 @@ class Solver {
 
     // HBM
     void *arena_ = nullptr;
-    bool arena_pooled_ = false;             // cudaMallocAsync from the device's default pool
+    bool arena_pooled_ = false;             // from this library's private per-device memory pool
     double *xbuf_[2] = {nullptr, nullptr};  // [0] = caller's x, [1] = ours
     double *gbuf_[2] = {nullptr, nullptr};
     double *d_ = nullptr, *pg_ = nullptr, *x_spare_ = nullptr;
@@ -167,6 +171,8 @@ class Solver {
     std::vector<GraphEntry> graphs_;
     cudaStream_t cap_stream_ = nullptr;
     bool graphs_enabled_ = true;     // LBFGSB200_GRAPHS=0 disables
+    bool small_enabled_ = true;      // LBFGSB200_SMALL=0 disables; cleared if the cluster launch is refused
+    int64_t ring_stride_ = 0;        // doubles between consecutive ring vectors (S_0, Y_0, S_1, ...)
     int64_t graph_replays_ = 0;
 
     // profile

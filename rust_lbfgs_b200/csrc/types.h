@@ -50,6 +50,7 @@ struct PeerCtx {
     double *mail_self;             // this rank's mailbox
     double *const *mail_table;     // device array: mail_table[r] = rank r's mailbox as mapped into this process
     double *extra[2];              // optional device scalars that ride along with the exchange (summed in place)
+    unsigned int *fault;           // communicator-owned device word, set when a peer did not answer in time
 };
 
 // Per-solver reduction workspace in HBM.

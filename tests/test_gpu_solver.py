@@ -454,3 +454,52 @@ def test_perturbed_x0_n1e8_vs_compensated_oracle(oracle):
     ex = float(np.max(np.abs(xg - ref["x"])) / np.max(np.abs(ref["x"])))
     print(f"n=1e8 perturbed x0: worst scalar deviation {worst:.3e}, final x deviation {ex:.3e}, evaluations {rep.neval}")
     assert worst <= 1e-10 and ex <= 1e-10
+
+
+# ---- the launch-bound regime: the cluster-persistent two-loop kernel vs the multi-kernel chain -------------------------
+@pytest.mark.parametrize("n", [2, 100, 2050, 10_001, 65_536, 131_074, 262_144])
+def test_small_n_cluster_two_loop_matches_the_chain(n, monkeypatch):
+    """k_two_loop_small (small.cu: all 2m trips in one thread-block cluster, q in shared memory, DSMEM reductions)
+    against the 2m-launch chain of k_backward / k_forward: same element-wise arithmetic, different summation tree,
+    so the trajectories agree to rounding (identical evaluation counts; x to 1e-11 over 30 iterations)."""
+    def run(small, builder, x0, evaluate):
+        monkeypatch.setenv("LBFGSB200_SMALL", "1" if small else "0")
+        return gpu_minimize(builder(), x0, evaluate, record_x=True)
+    even = n - (n % 2)
+    cases = [("defaults", lambda: R.lbfgs().with_max_iterations(30), perturbed_x0(even), R.Rosenbrock()),
+             ("m=1", lambda: R.lbfgs().with_m(1).with_max_iterations(20), perturbed_x0(even), R.Rosenbrock()),
+             ("m=20 damping", lambda: R.lbfgs().with_m(20).with_damping(True).with_linesearch_algorithm("BacktrackingStrongWolfe")
+              .with_max_iterations(30), perturbed_x0(even), R.Rosenbrock())]
+    if n >= 100:
+        cases.append(("owl-qn sub-range", lambda: R.lbfgs().with_orthantwise(0.5, 3, even - 5).with_max_iterations(30),
+                      perturbed_x0(even), R.Rosenbrock()))
+    if n % 2:   # odd length: a user evaluate (quadratic) — the Rosenbrock objective needs pairs
+        import torch
+        w = torch.linspace(0.5, 2.0, n, dtype=torch.float64, device="cuda:0")
+
+        def quad(x, gx):
+            gx.copy_(w * (x - 1.0))
+            return 0.5 * torch.sum(w * (x - 1.0) ** 2)
+        cases = [("odd n, user evaluate", lambda: R.lbfgs().with_max_iterations(15), np.linspace(-1.0, 2.0, n), quad)]
+    for name, builder, x0, evaluate in cases:
+        a = run(True, builder, x0, evaluate)
+        b = run(False, builder, x0, evaluate)
+        assert a["status_name"] == b["status_name"], (name, a["status_name"], b["status_name"], a["error"], b["error"])
+        assert len(a["trace"]) == len(b["trace"]) > 2, name
+        for s, t in zip(a["trace"], b["trace"]):
+            assert (s["neval"], s["ncall"]) == (t["neval"], t["ncall"]), (name, s["niter"])
+            assert np.max(np.abs(s["x"] - t["x"])) <= 1e-11 * np.max(np.abs(t["x"])), (name, s["niter"])
+            assert abs(s["fx"] - t["fx"]) <= 1e-11 * max(abs(t["fx"]), t["gnorm"] * t["xnorm"]), (name, s["niter"])
+
+
+def test_small_n_profile_counts_one_launch_per_update():
+    """At small n an iteration's update is 1 history / commit launch + ONE two-loop launch (no k_backward / k_forward)."""
+    import torch
+    x = torch.tensor(perturbed_x0(4096), device="cuda:0")
+    st = R.lbfgs().build(x, R.Rosenbrock())
+    for _ in range(10):
+        st.propagate()
+    prof = st.profile()
+    st.close()
+    assert prof["launches"]["update_small"] == 9 and prof["launches"]["commit"] == 9
+    assert prof["launches"]["backward"] == 0 and prof["launches"]["forward"] == 0
