@@ -144,7 +144,10 @@ typedef int (*lbfgsb200_trial_eval_fn)(void *user, const double *xp_dev, const d
  * IterationData::update's vector work (src/lbfgs.rs:640-656, :670-673) on the way:
  *   x = xp + step*d;  g = grad f(x);  s = x - xp;  y = g - gp
  *   out_dev[0..4] = partial s.s, y.s, y.y, s.(-g), s.(gp*bs_scale)      (bs_scale = -step_returned, for damping)
- * 3R 4W; per iteration 2t + 7 passes replace the fused trial's 4t + 6.  Element-wise arithmetic must be that of
+ * 3R 4W; per iteration 2t + 7 passes replace the fused trial's 4t + 6.  gp_dev is, by contract, the gradient at
+ * xp_dev as THIS objective computed it (its evaluate, fused trial or previous commit wrote it); an objective whose
+ * gradient is element-local may therefore recompute it from xp instead of reading it (the built-in Rosenbrock
+ * does: 2R 4W, 2t + 6 passes per iteration).  Element-wise arithmetic must be that of
  * the unfused kernels (no FMA), so that all three paths produce the same bits.  Same rules as lbfgsb200_eval_fn:
  * enqueue on `stream`, do not synchronise, non-zero = Err.  Not used for OWL-QN. */
 typedef int (*lbfgsb200_probe_fn)(void *user, const double *xp_dev, const double *d_dev, double step,
@@ -158,6 +161,7 @@ typedef int (*lbfgsb200_commit_fn)(void *user, const double *xp_dev, const doubl
                                               objectives do, in their kernels' epilogue, once
                                               lbfgsb200_objective_set_shard gave them the communicator); such a
                                               callback must fail on every rank or on none */
+#define LBFGSB200_FUSED_COMMIT_SKIPS_GP 2   /* commit recomputes gp from xp (accounting: 2R 4W instead of 3R 4W) */
 typedef struct lbfgsb200_fused_ops {
     int64_t struct_size;                /* sizeof(lbfgsb200_fused_ops_t) */
     lbfgsb200_trial_eval_fn trial;      /* one-pass trial that writes x and g */

@@ -26,6 +26,7 @@ STATUS_NAMES = {
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
 ABI_VERSION = 3
 FUSED_SUMS_OVER_RANKS = 1
+FUSED_COMMIT_SKIPS_GP = 2
 LS_MORETHUENTE, LS_BACKTRACKING_ARMIJO, LS_BACKTRACKING_WOLFE, LS_BACKTRACKING_STRONG_WOLFE = 0, 1, 2, 3
 UNIQUE_ID_BYTES = 128
 

@@ -55,6 +55,7 @@ lb::Launch prim_launch(const PrimCtx &c, void *stream, int64_t n, int nvec) {
     lb::Launch L;
     L.stream = (cudaStream_t)stream;
     L.max_grid = c.dev.sm_count * c.dev.blocks_per_sm;
+    L.max_grid_trial = c.dev.sm_count * c.dev.blocks_per_sm_trial;
     L.streaming = (double)n * 8.0 * nvec > 0.75 * (double)c.dev.l2_bytes;
     L.ws = c.ws;
     return L;

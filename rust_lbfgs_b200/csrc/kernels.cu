@@ -19,13 +19,14 @@ __device__ __forceinline__ double sgn(double v) {  // orthantwise.rs:174-180: 0 
     return (double)((v > 0.0) - (v < 0.0));
 }
 
-inline int grid_for(const Launch &L, int64_t n, int U) {
+inline int grid_for(const Launch &L, int64_t n, int U, bool trial_family = false) {
     if (L.sequential) return 1;
     const int64_t nv = n >> 1;
     const int64_t tile = (int64_t)kThreads * U;
     int64_t tiles = (nv + tile - 1) / tile;
+    const int64_t cap = trial_family ? L.max_grid_trial : L.max_grid;
     if (tiles < 1) tiles = 1;
-    if (tiles > L.max_grid) tiles = L.max_grid;
+    if (tiles > cap) tiles = cap;
     return (int)tiles;
 }
 // The reduction workspace of one reducing launch: with peers, this launch gets the next exchange sequence number
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_dot(DotOp<S> op, int64
     } while (0)
 
 void launch_dots(const Launch &L, const double *g, const double *d, const double *x, int64_t n, double *out) {
-    const int grid = grid_for(L, n, kUt);
+    const int grid = grid_for(L, n, kUt, /*trial_family=*/true);
     count(L);
     if (d) {
         LB_DISPATCH_S(L, (k_dots<true, true><<<grid, threads_for(L), 0, L.stream>>>({g, d, x}, n, ws_for(L), out)),

@@ -26,6 +26,7 @@ enum Kind { OBJ_ROSENBROCK = 0, OBJ_BOOTH = 1, OBJ_GLM = 2, OBJ_LJ = 3 };
 struct Objective {
     int kind = 0;
     bool sequential = false;     // LBFGSB200_REDUCE_SEQUENTIAL: f summed in the reference's order by one thread
+    bool recompute_gp = true;    // Rosenbrock commit: gp = grad f(xp) recomputed instead of read (LBFGSB200_COMMIT_RECOMPUTE_GP=0: read)
     DeviceInfo dev{};
     ReduceWs ws{};
     // GLM
@@ -138,17 +139,21 @@ struct RosenProbeOp {
     __device__ __forceinline__ void tail(int64_t, double (&)[4]) const {}
 };
 template <bool S>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_probe(RosenProbeOp<S> op, int64_t n, ReduceWs ws, double *out) {
+__global__ void __launch_bounds__(kThreads, kProbePrefetch ? 1 : kMinBlocks)
+k_rosenbrock_probe(RosenProbeOp<S> op, int64_t n, ReduceWs ws, double *out) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    stream_pairs<4, kUt>(n, op, acc);
+    if (kProbePrefetch) stream_pairs_prefetch<4, kUt>(n, op, acc);
+    else stream_pairs<4, kUt>(n, op, acc);
     grid_reduce<4>(acc, ws, out);
 }
 
 // Accepted point + history update in one pass (lbfgsb200_commit_fn): x = xp + step*d and g = grad f(x) are
 // recomputed with the probe's arithmetic (same bits as the accepted probe saw), written once, and
-// s = x - xp, y = g - gp and IterationData::update's sums come out of the same registers — 3R 4W replacing the
-// last trial's 2W and k_history's 4R 2W.  Tile shape and accumulation order are k_history's (kUh, history_elem).
-template <bool S>
+// s = x - xp, y = g - gp and IterationData::update's sums come out of the same registers — replacing the last
+// trial's 2W and k_history's 4R 2W.  Tile shape and accumulation order are k_history's (kUh, history_elem).
+// RECOMPUTE_GP: gp is by contract this objective's gradient at xp, and Rosenbrock's gradient is element-local, so
+// rosen_pair(xp) reproduces the stored gp bit for bit from a vector the kernel reads anyway: 2R 4W instead of 3R 4W.
+template <bool S, bool RECOMPUTE_GP>
 struct RosenCommitOp {
     const double *xp, *d, *gp;
     double *x, *g, *s, *y;
@@ -157,10 +162,11 @@ struct RosenCommitOp {
     __device__ __forceinline__ void load(Regs &r, int64_t i) const {
         r.xp = ld2<S>(xp, i);
         r.d = ld2<S>(d, i);
-        r.gp = ld2<S>(gp, i);
+        if (!RECOMPUTE_GP) r.gp = ld2<S>(gp, i);
     }
     __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[5]) const {
         double2 xo, o, so, yo;
+        if (RECOMPUTE_GP) rosen_pair(r.xp.x, r.xp.y, r.gp);
         xo.x = r.xp.x + step * r.d.x;                       // core.rs:156-157
         xo.y = r.xp.y + step * r.d.y;
         rosen_pair(xo.x, xo.y, o);
@@ -173,8 +179,9 @@ struct RosenCommitOp {
     }
     __device__ __forceinline__ void tail(int64_t, double (&)[5]) const {}
 };
-template <bool S>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) k_rosenbrock_commit(RosenCommitOp<S> op, int64_t n, ReduceWs ws, double *out) {
+template <bool S, bool RECOMPUTE_GP>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+k_rosenbrock_commit(RosenCommitOp<S, RECOMPUTE_GP> op, int64_t n, ReduceWs ws, double *out) {
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     stream_pairs<5, kUh>(n, op, acc);
     grid_reduce<5>(acc, ws, out);
@@ -627,7 +634,8 @@ inline int stream_grid(const Objective *o, int64_t n, int U = kU) {
     if (o->sequential) return 1;
     const int64_t tile = (int64_t)kThreads * U;
     int64_t tiles = ((n >> 1) + tile - 1) / tile;
-    const int64_t cap = (int64_t)o->dev.sm_count * o->dev.blocks_per_sm;
+    // the kUt family (evaluate, fused trial, probe — and the solver's K2) shares one grid so that all paths sum alike
+    const int64_t cap = (int64_t)o->dev.sm_count * (U == kUt ? o->dev.blocks_per_sm_trial : o->dev.blocks_per_sm);
     if (tiles > cap) tiles = cap;
     if (tiles < 1) tiles = 1;
     return (int)tiles;
@@ -683,8 +691,14 @@ int commit_impl(Objective *o, const double *xp, const double *d, const double *g
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     const int grid = stream_grid(o, n, kUh);
     const int threads = o->sequential ? 1 : kThreads;
-    if (rosen_streaming(o, n)) k_rosenbrock_commit<true><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
-    else k_rosenbrock_commit<false><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+    const bool st = rosen_streaming(o, n);
+    if (o->recompute_gp) {
+        if (st) k_rosenbrock_commit<true, true><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+        else k_rosenbrock_commit<false, true><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+    } else {
+        if (st) k_rosenbrock_commit<true, false><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+        else k_rosenbrock_commit<false, false><<<grid, threads, 0, stream>>>({xp, d, gp, x, g, s, y, step, bs_scale}, n, fused_ws(o), out);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
@@ -773,6 +787,8 @@ int make(int device, int kind, Objective **out) {
     if (cudaSetDevice(device) != cudaSuccess) { delete o; return LBFGSB200_ERR_CUDA; }
     rc = alloc_reduce_ws(o->dev, &o->ws);
     if (rc != 0) { delete o; return rc; }
+    const char *rg = getenv("LBFGSB200_COMMIT_RECOMPUTE_GP");
+    o->recompute_gp = !(rg && rg[0] == '0');
     *out = o;
     return 0;
 }
@@ -888,6 +904,7 @@ int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fu
         out->probe = lbfgsb200_objective_probe;
         out->commit = lbfgsb200_objective_commit;
         if (lb::sums_over_ranks(o)) out->flags |= LBFGSB200_FUSED_SUMS_OVER_RANKS;
+        if (o->recompute_gp) out->flags |= LBFGSB200_FUSED_COMMIT_SKIPS_GP;
     }
     return 0;
 }

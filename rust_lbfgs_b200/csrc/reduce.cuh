@@ -239,6 +239,65 @@ __device__ __forceinline__ void stream_pairs(int64_t n, Op &op, double (&acc)[NA
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.tail(n - 1, acc);
 }
 
+// The same walk with the NEXT tile's loads issued before the current tile is consumed (two register sets, the loop
+// unrolled by two so no register moves): for kernels with enough arithmetic per byte that "load a tile, then
+// compute on it" leaves the memory pipe idle during the compute phase (the Rosenbrock probe: ~25 flops per 32
+// bytes, all 8 warps of the one resident CTA in the same phase).  Same element -> thread map and the same
+// accumulation order as stream_pairs, hence the same bits.
+template <int NACC, int U, class Op>
+__device__ __forceinline__ void stream_pairs_prefetch(int64_t n, Op &op, double (&acc)[NACC]) {
+    const int64_t nv = n >> 1;
+    if (blockDim.x == 1) {
+        stream_pairs<NACC, U>(n, op, acc);
+        return;
+    }
+    constexpr int64_t kTile = (int64_t)kThreads * U;
+    const int64_t stride = (int64_t)gridDim.x * kTile;
+    int64_t base = (int64_t)blockIdx.x * kTile;
+    typename Op::Regs ra[U], rb[U];
+    bool full = base + kTile <= nv;
+    if (full) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) op.load(ra[u], base + u * kThreads + threadIdx.x);
+    }
+    while (full) {
+        int64_t next = base + stride;
+        bool next_full = next + kTile <= nv;
+        if (next_full) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) op.load(rb[u], next + u * kThreads + threadIdx.x);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) op.apply(ra[u], base + u * kThreads + threadIdx.x, acc);
+        base = next;
+        full = next_full;
+        if (!full) break;
+        next = base + stride;
+        next_full = next + kTile <= nv;
+        if (next_full) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) op.load(ra[u], next + u * kThreads + threadIdx.x);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) op.apply(rb[u], base + u * kThreads + threadIdx.x, acc);
+        base = next;
+        full = next_full;
+    }
+    if (base < nv) {   // this CTA's last, partial tile
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < nv) op.load(ra[u], i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < nv) op.apply(ra[u], i, acc);
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.tail(n - 1, acc);
+}
+
 // IterationData::update for one element (src/lbfgs.rs:644-656, :670-673).  Shared by k_history and by the objectives'
 // commit kernels (lbfgsb200_commit_fn), so the fused and the unfused paths accumulate the same terms.
 template <bool DAMP, bool OWL>

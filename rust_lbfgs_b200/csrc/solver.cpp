@@ -41,6 +41,9 @@ int query_device(int device, DeviceInfo *out) {
     out->blocks_per_sm = env_int("LBFGSB200_BLOCKS_PER_SM", 1);  // tuned: see types.h
     if (out->blocks_per_sm < 1) out->blocks_per_sm = 1;
     if (out->blocks_per_sm > 16) out->blocks_per_sm = 16;
+    out->blocks_per_sm_trial = env_int("LBFGSB200_TRIAL_BLOCKS_PER_SM", 1);
+    if (out->blocks_per_sm_trial < 1) out->blocks_per_sm_trial = 1;
+    if (out->blocks_per_sm_trial > 16) out->blocks_per_sm_trial = 16;
     return 0;
 }
 
@@ -314,6 +317,7 @@ Launch Solver::launch_cfg() {
     Launch L;
     L.stream = stream_;
     L.max_grid = dev_.sm_count * dev_.blocks_per_sm;
+    L.max_grid_trial = dev_.sm_count * dev_.blocks_per_sm_trial;
     L.streaming = streaming_;
     L.sequential = sequential_;
     L.ws = ws_;
@@ -594,7 +598,7 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
         prof_begin(LBFGSB200_K_COMMIT);
         const int erc = fused_.commit(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
                                       Y_[slot_new], n_, (void *)L.stream, hist);
-        prof_end(LBFGSB200_K_COMMIT, 7.0 * vbytes);
+        prof_end(LBFGSB200_K_COMMIT, ((fused_.flags & LBFGSB200_FUSED_COMMIT_SKIPS_GP) ? 6.0 : 7.0) * vbytes);
         launch_counter_ += 1;
         if (erc != 0) return fail(erc <= LBFGSB200_ERR_CUDA ? erc : LBFGSB200_ERR_EVALUATE, "the objective's commit failed");
         rc = reduce_across_ranks(SLOT_HIST, 5, /*ours=*/fused_exchanges());

@@ -24,6 +24,10 @@ constexpr int kWarps = kThreads / 32;
 #endif
 constexpr int kUt = LB_UT;             // the same for the fused trial kernel (2R 2W) and, so that the fused and the
                                        // unfused paths sum the same terms in the same order, K2 and the objective
+#ifndef LB_PROBE_PREFETCH
+#define LB_PROBE_PREFETCH 0
+#endif
+constexpr bool kProbePrefetch = LB_PROBE_PREFETCH != 0;   // software-pipelined tile walk for the write-free probe
 constexpr int kUh = LB_UH;             // the same for the history kernel (5 input vectors)
 // Tile shapes, tuned on B200 at n = 1e8 (profiles/r01_tuning.md): one 256-thread CTA per SM with 8 independent
 // 128-bit loads per input vector in flight per thread (2048 per SM per vector) streams 3R 1W at ~7.0 TB/s; more

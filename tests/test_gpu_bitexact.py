@@ -63,6 +63,27 @@ def test_p2_p3_rosenbrock_then_owlqn_bit_exact(oracle):
         assert np.array_equal(np.sign(a["x"]), np.sign(b["x"]))
 
 
+def test_p7_recorded_rust_trajectory_on_the_gpu(oracle):
+    """tests/simple.rs:33-35, :48-50 — the trajectory the reference's authors recorded from executed Rust (before the
+    step-size cap existed; see tests/test_oracle_pins.py::test_p7...).  The CUDA path in reference-order mode lands on
+    the same 17-digit values after 37 + 171 iterations."""
+    got = gpu_minimize(seq().with_max_step_size(1e20), rosenbrock_x0(100), R.Rosenbrock())
+    t = got["trace"][-1]
+    assert got["status_name"] == "OK_CONVERGED" and len(got["trace"]) == 38
+    assert repr(float(got["report"].fx)) == "1.2832127771605377e-15"
+    assert repr(float(got["x"][0])) == "0.9999999960382451" and repr(float(got["x"][1])) == "0.9999999917607568"
+    assert repr(float(t["xnorm"])) == "9.999999938995018" and repr(float(t["gnorm"])) == "9.486547293218877e-07"
+    got2 = gpu_minimize(seq().with_max_step_size(1e20).with_orthantwise(1.0, 0, 99), got["x"], R.Rosenbrock())
+    t2 = got2["trace"][-1]
+    assert got2["status_name"] == "OK_CONVERGED" and len(got2["trace"]) == 172
+    assert repr(float(got2["report"].fx)) == "43.50249999999999"
+    assert repr(float(got2["x"][0])) == "0.2500000069348678" and repr(float(got2["x"][1])) == "0.057500004213084016"
+    assert repr(float(t2["xnorm"])) == "1.8806931246657475" and repr(float(t2["gnorm"])) == "1.12236896804755e-06"
+    # the production (tree-sum) path reaches the same point to 1e-9 with the same iteration counts
+    tree = gpu_minimize(R.lbfgs().with_max_step_size(1e20), rosenbrock_x0(100), R.Rosenbrock())
+    assert len(tree["trace"]) == 38 and abs(tree["x"][0] - 0.9999999960382451) <= 1e-9
+
+
 def test_p4_booth_bit_exact(oracle):
     ref = oracle_run(oracle, [-1.2, 1.0], "booth")                                     # tests/simple.rs:57-83
     got = gpu_minimize(seq(), [-1.2, 1.0], R.Booth())
@@ -256,8 +277,11 @@ def test_fused_trial_kernel_direct(oracle):
         torch.cuda.synchronize()
         assert np.array_equal(host(out2)[:4], o[:4]), n
         # the commit: x, g as the trial wrote them; s = x - xp, y = g - gp bit-exact; the sums of lbfgsb200_history_update
-        gp = rng.standard_normal(n)
-        gpd = dev(gp)
+        # gp is by contract the objective's own gradient at xp (the built-in commit recomputes it from xp)
+        gpd, fdummy = torch.empty(n, dtype=torch.float64, device="cuda:0"), torch.zeros(1, dtype=torch.float64, device="cuda:0")
+        ck(L.lbfgsb200_objective_eval(obj._user_ptr(0), xpd.data_ptr(), gpd.data_ptr(), n, stream(), fdummy.data_ptr()))
+        torch.cuda.synchronize()
+        gp = host(gpd)
         x2, g2, s2, y2 = (torch.empty(n, dtype=torch.float64, device="cuda:0") for _ in range(4))
         out3 = torch.zeros(8, dtype=torch.float64, device="cuda:0")
         ck(L.lbfgsb200_objective_commit(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), gpd.data_ptr(), step, -0.41,
@@ -276,6 +300,6 @@ def test_fused_trial_kernel_direct(oracle):
     ck(L.lbfgsb200_objective_fused_ops(lj._user_ptr(0), C.byref(ops)))
     assert not ops.trial and not ops.probe and not ops.commit
     ck(L.lbfgsb200_objective_fused_ops(obj._user_ptr(0), C.byref(ops)))
-    assert ops.trial and ops.probe and ops.commit and ops.flags == 0
+    assert ops.trial and ops.probe and ops.commit and ops.flags == R._lib.FUSED_COMMIT_SKIPS_GP
     assert L.lbfgsb200_objective_has_trial_eval(lj._user_ptr(0)) == 0
     assert L.lbfgsb200_objective_has_trial_eval(obj._user_ptr(0)) == 1

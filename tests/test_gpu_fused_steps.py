@@ -217,9 +217,12 @@ def test_probe_and_commit_random(oracle, n):
     (src/core.rs:155-164, src/lib.rs:79-94, src/lbfgs.rs:644-647); the probe's and the commit's sums."""
     import torch
     L, O = R.lib(), oracle.lib()
-    xp, d, gp = gpu_rand(n, 15), gpu_rand(n, 16, 0.1), gpu_rand(n, 17)
+    xp, d = gpu_rand(n, 15), gpu_rand(n, 16, 0.1)
     step, bs_scale = 0.59375, -0.71875
     obj = R.Rosenbrock()
+    # gp is by contract the objective's own gradient at xp (the built-in commit recomputes it instead of reading it)
+    gp, f0 = torch.empty_like(xp), torch.zeros(1, dtype=torch.float64, device="cuda:0")
+    ck(L.lbfgsb200_objective_eval(obj._user_ptr(0), xp.data_ptr(), gp.data_ptr(), n, stream(), f0.data_ptr()))
     out = torch.zeros(8, dtype=torch.float64, device="cuda:0")
     ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xp.data_ptr(), d.data_ptr(), step, n, stream(), out.data_ptr()))
     x, g, s, y = (torch.empty_like(xp) for _ in range(4))

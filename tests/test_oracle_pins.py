@@ -55,6 +55,34 @@ def test_p2_p3_rosenbrock_then_owlqn(oracle):
     assert len(r2["trace"]) == 150 and r2["report"]["neval"] == 338
 
 
+def test_p7_recorded_rust_trajectory_digit_for_digit(oracle):
+    """The only EXECUTED-Rust trajectory the reference records: the comments at tests/simple.rs:33-35 ("Iteration 37:
+    fx = 0.0000000000000012832127771605377, x[0] = 0.9999999960382451, x[1] = 0.9999999917607568, xnorm =
+    9.999999938995018, gnorm = 0.0000009486547293218877, step = 1") and :48-50 ("Iteration 171: fx = 43.50249999999999,
+    x[0] = 0.2500000069348678, x[1] = 0.057500004213084016, xnorm = 1.8806931246657475, gnorm =
+    0.00000112236896804755, step = 1").  They predate the step-size cap (`max_step_size`, src/lbfgs.rs:547-551: the
+    first trial of every search now satisfies |step * d| <= 1): with the cap lifted the oracle reproduces every
+    printed digit — 17 significant digits, i.e. bit-identical doubles after 37 MoreThuente and 171 OWL-QN
+    iterations (two-loop recursion, history update, both line searches, pseudo-gradient, orthant projection).  The
+    iteration counter reads one more (38 / 172): the no-op first propagate (src/lbfgs.rs:507-510) is counted today.
+    scripts/explain_iteration_counts.py shows the hypotheses that do NOT reproduce it."""
+    r = oracle.minimize(oracle.default_param(max_step_size=1e20), rosenbrock_x0(100), oracle.Objective.builtin("rosenbrock"))
+    t = r["trace"][-1]
+    assert r["status_name"] == "OK_CONVERGED" and len(r["trace"]) == 38
+    assert repr(float(r["report"]["fx"])) == "1.2832127771605377e-15"
+    assert repr(float(r["x"][0])) == "0.9999999960382451" and repr(float(r["x"][1])) == "0.9999999917607568"
+    assert repr(float(t["xnorm"])) == "9.999999938995018" and repr(float(t["gnorm"])) == "9.486547293218877e-07"
+    assert t["step"] == 1.0
+    p = oracle.default_param(orthantwise=1, owl_c=1.0, owl_start=0, owl_end=99, max_step_size=1e20)
+    r2 = oracle.minimize(p, r["x"].copy(), oracle.Objective.builtin("rosenbrock"))
+    t2 = r2["trace"][-1]
+    assert r2["status_name"] == "OK_CONVERGED" and len(r2["trace"]) == 172
+    assert repr(float(r2["report"]["fx"])) == "43.50249999999999"
+    assert repr(float(r2["x"][0])) == "0.2500000069348678" and repr(float(r2["x"][1])) == "0.057500004213084016"
+    assert repr(float(t2["xnorm"])) == "1.8806931246657475" and repr(float(t2["gnorm"])) == "1.12236896804755e-06"
+    assert t2["step"] == 1.0
+
+
 def test_p4_booth(oracle):
     """tests/simple.rs:57-83."""
     r = oracle.minimize(oracle.default_param(), np.array([-1.2, 1.0]), oracle.Objective.builtin("booth"))
