@@ -370,6 +370,11 @@ int  lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const do
                              int64_t ncol, lbfgsb200_objective_t **out);
 /* all-pairs Lennard-Jones  examples/lj.rs:20-64,114-117; n = 3 * atoms */
 int  lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, lbfgsb200_objective_t **out);
+/* Lennard-Jones per-pair arithmetic.  0 (default): the reference's — sqrt, sigma/r, powi, g*dr/r with IEEE
+ * divisions (examples/lj.rs:23-32,50-57), so every pair term has the reference's bits.  1: the molecular-dynamics
+ * form — only 1/r^2 (reciprocal seed + two Newton steps), fused multiply-adds; ~2.5x fewer FP64 instructions,
+ * every pair term within a few ulp of the reference's.  Ignored (always 0) with LBFGSB200_REDUCE_SEQUENTIAL. */
+int  lbfgsb200_objective_set_lj_fast(lbfgsb200_objective_t *objective, int fast);
 void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective);
 /* LBFGSB200_REDUCE_* for the objective's own sum (f); SEQUENTIAL is implemented for Rosenbrock, Booth and
  * Lennard-Jones (exp/log in the GLMs are not bit-reproducible against a CPU libm anyway) */

@@ -165,6 +165,7 @@ def lib():
     _sig(L, "lbfgsb200_objective_glm", i32, [i32, i32, vp, vp, i64, i64, pp(vp)])
     _sig(L, "lbfgsb200_objective_lennard_jones", i32, [i32, dbl, dbl, pp(vp)])
     _sig(L, "lbfgsb200_objective_set_reduction", i32, [vp, i32])
+    _sig(L, "lbfgsb200_objective_set_lj_fast", i32, [vp, i32])
     _sig(L, "lbfgsb200_objective_set_shard", i32, [vp, vp, pp(i64)])
     _sig(L, "lbfgsb200_objective_has_trial_eval", i32, [vp])
     _sig(L, "lbfgsb200_objective_trial_eval", i32, [vp, vp, vp, dbl, vp, vp, i64, vp, vp])

@@ -12,7 +12,7 @@ namespace lb {
 struct Launch {
     cudaStream_t stream = nullptr;
     int max_grid = 148 * 8;   // CTAs: a multiple of the SM count (set from the device at create)
-    int max_grid_trial = 148; // the same for K2, which shares its grid with the objectives' trial-family kernels
+    int max_grid_trial = 148 * 2; // the same for K2, which shares its grid with the objectives' trial-family kernels
     bool streaming = true;    // evict-first loads/stores (vectors much larger than L2)
     bool sequential = false;  // reference-order reductions: every kernel runs as <<<1, 1>>> (validation only)
     ReduceWs ws{};            // level-2 reduction workspace (+ the peer mailboxes when sharded over GPUs)

@@ -40,6 +40,7 @@ struct Objective {
     bool fused = true;           // LBFGSB200_GLM_FUSED=0 forces the two-pass kernels
     // LJ
     double eps = 1.0, sigma = 1.0;
+    bool lj_fast = false;        // lj_pair_fast instead of the reference's per-pair arithmetic (opt-in)
     // multi-GPU (lbfgsb200_objective_set_shard)
     Comm *comm = nullptr;            // GLM: rows of X sharded, f and g summed over ranks; LJ: atoms sharded
     std::vector<int64_t> offsets;    // LJ: element offsets of every rank's shard (nranks + 1)
@@ -488,10 +489,12 @@ int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, dou
     return LBFGSB200_ERR_UNSUPPORTED;
 }
 
-// ---- Lennard-Jones: thread = atom, partners streamed through shared memory in index order -----
+// ---- Lennard-Jones: all pairs, FP64-pipe bound -------------------------------------------------------------
 // For atom i the reference adds its pair forces in ascending partner order (pairs (i, j<i) during
 // row i, then pairs (i', i) for i' > i), and (p_i - p_j) == -(p_j - p_i) exactly, so a sequential
-// ascending loop over all partners reproduces forces[i] bit for bit.
+// ascending loop over all partners reproduces forces[i] bit for bit (k_lj: one thread per atom, used for
+// reference-order validation).  The production kernel (k_lj_lanes) spreads the partners of an atom over P lanes
+// and combines them with a fixed butterfly: same per-pair arithmetic, different association.
 constexpr int kLjTile = 256;
 
 // a / b from the correctly rounded reciprocal y = RN(1 / b): q = RN(a y); rem = a - b q (exact, one FMA);
@@ -503,9 +506,54 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
     const double rem = __fma_rn(-b, q, a);
     return __fma_rn(rem, y, q);
 }
+
+// One ordered pair in the REFERENCE's arithmetic (examples/lj.rs:23-32,50-57): d = p_i - p_j, `other` = (j != i).
+// pe = pair energy; (c0, c1, c2) = the pair's contribution to forces[i].
+__device__ __forceinline__ void lj_pair_ref(double d0, double d1, double d2, bool other, double eps, double sigma,
+                                            double &pe, double &c0, double &c1, double &c2) {
+    const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+    const double r = sqrt(other ? r2 : 1.0);                  // vecdist, lj.rs:50 (self pair: masked by the caller)
+    const double y = 1.0 / r;                                 // the one true division of the pair
+    const double qq = div_by(sigma, r, y);
+    const double q2 = qq * qq;
+    const double s6 = q2 * (q2 * q2);                         // powi(sigma/r, 6), lj.rs:23,30
+    pe = 4.0 * eps * (s6 * s6 - s6);                          // pair_energy, lj.rs:51
+    const double gr = div_by(24.0 * eps * (s6 - 2.0 * (s6 * s6)), r, y);  // pair_gradient, lj.rs:32
+    // forces[i][k] += g*dr/r with dr = p_j - p_i = -d  (lj.rs:55-57)
+    c0 = div_by(gr * (-d0), r, y);
+    c1 = div_by(gr * (-d1), r, y);
+    c2 = div_by(gr * (-d2), r, y);
+}
+
+// The same pair in the arithmetic a molecular-dynamics code would use (opt-in: lbfgsb200_objective_set_lj_fast):
+// only 1/r^2 is needed — (sigma/r)^6 = (sigma^2/r^2)^3 and g*dr/r = 24 eps (s6 - 2 s12) dr / r^2 — so the square
+// root and five of the six divisions disappear; 1/r^2 comes from the SFU's reciprocal seed and two Newton steps
+// (full double precision, not correctly rounded), and multiply-adds are fused.  ~23 FP64 instructions per pair
+// instead of ~60; every pair term agrees with the reference's to a few ulp.
+__device__ __forceinline__ double rcp_newton(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));     // ~20 good bits (MUFU.RCP64H)
+    double e = __fma_rn(-a, y, 1.0);
+    y = __fma_rn(y, e, y);                                    // ~40 bits
+    e = __fma_rn(-a, y, 1.0);
+    return __fma_rn(y, e, y);                                 // full precision
+}
+__device__ __forceinline__ void lj_pair_fast(double d0, double d1, double d2, bool other, double eps4, double eps24,
+                                             double sigma2, double &pe, double &c0, double &c1, double &c2) {
+    const double r2 = __fma_rn(d2, d2, __fma_rn(d1, d1, d0 * d0));
+    const double inv = rcp_newton(other ? r2 : 1.0);
+    const double s2 = sigma2 * inv;
+    const double s6 = s2 * s2 * s2;
+    pe = eps4 * __fma_rn(s6, s6, -s6);
+    const double w = eps24 * __fma_rn(-2.0 * s6, s6, s6) * inv;
+    c0 = w * (-d0);
+    c1 = w * (-d1);
+    c2 = w * (-d2);
+}
+
+// Thread = atom, partners in ascending order: forces bit-identical to the reference's (validation / SEQUENTIAL).
 // Sharded over GPUs: x holds ALL natoms positions (gathered), this rank owns atoms [a0, a0 + nloc) and writes
-// their gradient to g[0 .. 3 nloc); partners are still visited in ascending global order, so the forces are the
-// same bits as on one GPU.
+// their gradient to g[0 .. 3 nloc).
 __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
                                                 int64_t a0, int64_t nloc, double eps, double sigma, ReduceWs ws, double *fx) {
     __shared__ double sp[kLjTile * 3];
@@ -527,17 +575,8 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
         for (int jj = 0; jj < (int)cnt; ++jj) {
             const int64_t j = base + jj;
             const bool other = (j != i);
-            const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
-            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
-            const double r = sqrt(other ? r2 : 1.0);                  // vecdist, lj.rs:50 (self pair: masked below)
-            const double y = 1.0 / r;                                 // the one true division of the pair
-            const double qq = div_by(sigma, r, y);
-            const double q2 = qq * qq;
-            const double s6 = q2 * (q2 * q2);                         // powi(sigma/r, 6), lj.rs:23,30
-            const double pe = 4.0 * eps * (s6 * s6 - s6);             // pair_energy, lj.rs:51
-            const double gr = div_by(24.0 * eps * (s6 - 2.0 * (s6 * s6)), r, y);  // pair_gradient, lj.rs:32
-            // forces[i][k] += g*dr/r with dr = p_j - p_i = -d  (lj.rs:55-57)
-            const double c0 = div_by(gr * (-d0), r, y), c1 = div_by(gr * (-d1), r, y), c2 = div_by(gr * (-d2), r, y);
+            double pe, c0, c1, c2;
+            lj_pair_ref(pi0 - sp[3 * jj], pi1 - sp[3 * jj + 1], pi2 - sp[3 * jj + 2], other, eps, sigma, pe, c0, c1, c2);
             if (j < i) e += pe;                                       // counted once
             if (other) { f0 += c0; f1 += c1; f2 += c2; }
         }
@@ -551,12 +590,14 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
     grid_reduce<1>(acc, ws, fx);
 }
 
-// Sharded over GPUs a rank owns only N/P atoms — too few threads for one thread per atom — so P lanes of a warp
-// share an atom: lane `sub` visits partners sub, sub + P, ... of every tile (ascending), and the P partial forces
-// are combined with a fixed xor-butterfly.  Deterministic, but the association differs from the one-thread
-// order, so forces agree with the one-GPU kernel to rounding (1e-16 relative), not bit for bit.
-template <int P>
-__global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
+// The production kernel: P lanes of a warp share an atom.  Lane `sub` visits partners sub, sub + P, ... of every
+// tile (ascending), and the P partial forces are combined with a fixed xor-butterfly — deterministic, but the
+// association differs from the one-thread order, so forces agree with k_lj to rounding (1e-16 relative), not bit
+// for bit.  P is chosen so that the grid has >= 16 CTAs per SM: one thread per atom gives 1e5 atoms only 2.7 CTAs
+// per SM (30 % of the warps a B200 can hold, and a 3-vs-2 CTA imbalance between SMs); with 8 lanes per atom the
+// FP64 pipe — the roofline of this kernel — stays busy.  FAST selects lj_pair_fast.
+template <int P, bool FAST>
+__global__ void __launch_bounds__(kLjTile) k_lj_lanes(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
                                                       int64_t a0, int64_t nloc, double eps, double sigma, ReduceWs ws,
                                                       double *fx) {
     __shared__ double sp[kLjTile * 3];
@@ -567,6 +608,7 @@ __global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__
     const bool active = il < nloc;
     double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
     if (active) { pi0 = x[3 * i]; pi1 = x[3 * i + 1]; pi2 = x[3 * i + 2]; }
+    const double eps4 = 4.0 * eps, eps24 = 24.0 * eps, sigma2 = sigma * sigma;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
     for (int64_t base = 0; base < natoms; base += kLjTile) {
         const int64_t cnt = (natoms - base < kLjTile) ? (natoms - base) : kLjTile;
@@ -579,15 +621,9 @@ __global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__
             const int64_t j = base + jj;
             const bool other = (j != i);
             const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
-            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
-            const double r = sqrt(other ? r2 : 1.0);
-            const double y = 1.0 / r;
-            const double qq = div_by(sigma, r, y);
-            const double q2 = qq * qq;
-            const double s6 = q2 * (q2 * q2);
-            const double pe = 4.0 * eps * (s6 * s6 - s6);
-            const double gr = div_by(24.0 * eps * (s6 - 2.0 * (s6 * s6)), r, y);
-            const double c0 = div_by(gr * (-d0), r, y), c1 = div_by(gr * (-d1), r, y), c2 = div_by(gr * (-d2), r, y);
+            double pe, c0, c1, c2;
+            if (FAST) lj_pair_fast(d0, d1, d2, other, eps4, eps24, sigma2, pe, c0, c1, c2);
+            else lj_pair_ref(d0, d1, d2, other, eps, sigma, pe, c0, c1, c2);
             if (j < i) e += pe;
             if (other) { f0 += c0; f1 += c1; f2 += c2; }
         }
@@ -608,9 +644,45 @@ __global__ void __launch_bounds__(kLjTile) k_lj_split(const double *__restrict__
 }
 
 template <int P>
-void launch_lj_split(Objective *o, double *g, int64_t natoms, int64_t a0, int64_t nloc, cudaStream_t stream, double *fx) {
+void launch_lj_lanes(Objective *o, const double *x, double *g, int64_t natoms, int64_t a0, int64_t nloc, cudaStream_t stream,
+                     double *fx) {
     const int64_t blocks = (nloc + kLjTile / P - 1) / (kLjTile / P);
-    k_lj_split<P><<<(int)blocks, kLjTile, 0, stream>>>(o->xall, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx);
+    if (o->lj_fast) k_lj_lanes<P, true><<<(int)blocks, kLjTile, 0, stream>>>(x, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx);
+    else k_lj_lanes<P, false><<<(int)blocks, kLjTile, 0, stream>>>(x, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx);
+}
+
+// Lanes per atom: the smallest power of two that gives the grid >= 16 CTAs per SM (at most a warp per atom).
+inline int lj_lanes(const Objective *o, int64_t nloc) {
+    const int64_t want = (int64_t)o->dev.sm_count * 16 * kLjTile;
+    int P = 1;
+    while (P < 32 && nloc * P < want) P *= 2;
+    return P;
+}
+// The level-2 reduction workspace must hold one partial per CTA: grow it for large systems.
+inline int lj_ensure_ws(Objective *o, int64_t blocks) {
+    if (blocks <= o->ws.stride) return 0;
+    ReduceWs bigger{};
+    bigger.stride = (int)blocks;
+    if (cudaMalloc((void **)&bigger.partials, sizeof(double) * kMaxAcc * (size_t)bigger.stride) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    cudaFree(o->ws.partials);       // synchronises: nothing of ours is still running on the old workspace
+    o->ws.partials = bigger.partials;
+    o->ws.stride = bigger.stride;
+    return 0;
+}
+int launch_lj(Objective *o, const double *x, double *g, int64_t natoms, int64_t a0, int64_t nloc, cudaStream_t stream, double *fx) {
+    const int P = o->sequential ? 1 : lj_lanes(o, nloc);
+    const int64_t blocks = (nloc * P + kLjTile - 1) / kLjTile;
+    const int rc = lj_ensure_ws(o, blocks);
+    if (rc != 0) return rc;
+    switch (P) {
+        case 1: k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx); break;
+        case 2: launch_lj_lanes<2>(o, x, g, natoms, a0, nloc, stream, fx); break;
+        case 4: launch_lj_lanes<4>(o, x, g, natoms, a0, nloc, stream, fx); break;
+        case 8: launch_lj_lanes<8>(o, x, g, natoms, a0, nloc, stream, fx); break;
+        case 16: launch_lj_lanes<16>(o, x, g, natoms, a0, nloc, stream, fx); break;
+        default: launch_lj_lanes<32>(o, x, g, natoms, a0, nloc, stream, fx); break;
+    }
+    return 0;
 }
 
 // Reference-order energy (LBFGSB200_REDUCE_SEQUENTIAL): one thread walks the pairs (i, j < i) exactly as
@@ -737,29 +809,17 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
         case OBJ_LJ: {
             if (n % 3 != 0 || n < 3) return LBFGSB200_ERR_INVALID_PARAM;
             const int64_t nloc = n / 3;
-            const int64_t blocks = (nloc + kLjTile - 1) / kLjTile;
-            if (blocks > o->ws.stride) return LBFGSB200_ERR_INVALID_PARAM;
             if (o->comm && comm_size(o->comm) > 1) {  // atoms sharded: gather all positions, forces stay local
                 const int r = comm_rank(o->comm);
                 if (o->offsets[r + 1] - o->offsets[r] != n) return LBFGSB200_ERR_INVALID_PARAM;
                 const int grc = comm_allgatherv(o->comm, x, o->xall, o->offsets.data(), stream);
                 if (grc != 0) return grc;
-                // lanes per atom: enough threads to fill the GPU (~4 CTAs of 256 per SM), capped by the workspace
-                const int64_t natoms = o->offsets.back() / 3, a0 = o->offsets[r] / 3;
-                const int64_t want = (int64_t)o->dev.sm_count * 4 * kLjTile;
-                int P = 1;
-                while (P < 32 && nloc * P < want && (nloc * 2 * P + kLjTile - 1) / kLjTile <= o->ws.stride) P *= 2;
-                switch (P) {
-                    case 1: k_lj<<<(int)blocks, kLjTile, 0, stream>>>(o->xall, g, natoms, a0, nloc, o->eps, o->sigma, o->ws, fx); break;
-                    case 2: launch_lj_split<2>(o, g, natoms, a0, nloc, stream, fx); break;
-                    case 4: launch_lj_split<4>(o, g, natoms, a0, nloc, stream, fx); break;
-                    case 8: launch_lj_split<8>(o, g, natoms, a0, nloc, stream, fx); break;
-                    case 16: launch_lj_split<16>(o, g, natoms, a0, nloc, stream, fx); break;
-                    default: launch_lj_split<32>(o, g, natoms, a0, nloc, stream, fx); break;
-                }
+                const int lrc = launch_lj(o, o->xall, g, o->offsets.back() / 3, o->offsets[r] / 3, nloc, stream, fx);
+                if (lrc != 0) return lrc;
                 break;
             }
-            k_lj<<<(int)blocks, kLjTile, 0, stream>>>(x, g, nloc, 0, nloc, o->eps, o->sigma, o->ws, fx);
+            const int lrc = launch_lj(o, x, g, nloc, 0, nloc, stream, fx);
+            if (lrc != 0) return lrc;
             if (o->sequential) k_lj_energy_seq<<<1, 1, 0, stream>>>(x, nloc, o->eps, o->sigma, fx);
             break;
         }
@@ -846,6 +906,12 @@ int lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int redu
     if (!o || (reduction != LBFGSB200_REDUCE_TREE && reduction != LBFGSB200_REDUCE_SEQUENTIAL)) return LBFGSB200_ERR_INVALID_PARAM;
     if (reduction == LBFGSB200_REDUCE_SEQUENTIAL && o->kind == lb::OBJ_GLM) return LBFGSB200_ERR_UNSUPPORTED;
     o->sequential = reduction == LBFGSB200_REDUCE_SEQUENTIAL;
+    return 0;
+}
+int lbfgsb200_objective_set_lj_fast(lbfgsb200_objective_t *objective, int fast) {
+    lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
+    if (!o || o->kind != lb::OBJ_LJ) return LBFGSB200_ERR_INVALID_PARAM;
+    o->lj_fast = fast != 0;
     return 0;
 }
 int lbfgsb200_objective_set_shard(lbfgsb200_objective_t *objective, lbfgsb200_comm_t *comm, const int64_t *shard_offsets) {

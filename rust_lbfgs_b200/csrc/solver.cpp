@@ -41,7 +41,10 @@ int query_device(int device, DeviceInfo *out) {
     out->blocks_per_sm = env_int("LBFGSB200_BLOCKS_PER_SM", 1);  // tuned: see types.h
     if (out->blocks_per_sm < 1) out->blocks_per_sm = 1;
     if (out->blocks_per_sm > 16) out->blocks_per_sm = 16;
-    out->blocks_per_sm_trial = env_int("LBFGSB200_TRIAL_BLOCKS_PER_SM", 1);
+    // the write-free probe carries ~25 flops per 32 bytes: with ONE resident CTA all 8 warps load, then all
+    // compute, and the memory pipe idles meanwhile; two co-resident CTAs de-phase (measured at n = 1e8: 6.07 ->
+    // 6.80 TB/s; a register-prefetching single CTA gives the same 6.81, profiles/r02_tuning.md)
+    out->blocks_per_sm_trial = env_int("LBFGSB200_TRIAL_BLOCKS_PER_SM", 2);
     if (out->blocks_per_sm_trial < 1) out->blocks_per_sm_trial = 1;
     if (out->blocks_per_sm_trial > 16) out->blocks_per_sm_trial = 16;
     return 0;

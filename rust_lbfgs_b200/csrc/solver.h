@@ -38,7 +38,7 @@ struct DeviceInfo {
     int sm_count = 148;
     int64_t l2_bytes = 126ll << 20;
     int blocks_per_sm = 1;   // CTAs per SM in a full grid (LBFGSB200_BLOCKS_PER_SM); tuned, see types.h
-    int blocks_per_sm_trial = 1;   // the same for the line-search trial family: K2, evaluate, fused trial, probe
+    int blocks_per_sm_trial = 2;   // the same for the line-search trial family: K2, evaluate, fused trial, probe
                                    // (LBFGSB200_TRIAL_BLOCKS_PER_SM)
 };
 int query_device(int device, DeviceInfo *out);

@@ -98,8 +98,11 @@ class Objective {
     // tests/simple.rs:65-74
     static Objective booth(int device = 0) { Objective o; check(lbfgsb200_objective_booth(device, &o.h_)); return o; }
     // examples/lj.rs:20-64
-    static Objective lennard_jones(double epsilon = 1.0, double sigma = 1.0, int device = 0) {
-        Objective o; check(lbfgsb200_objective_lennard_jones(device, epsilon, sigma, &o.h_)); return o;
+    // fast: the 1/r^2 form with fused multiply-adds instead of the reference's per-pair arithmetic (a few ulp apart)
+    static Objective lennard_jones(double epsilon = 1.0, double sigma = 1.0, int device = 0, bool fast = false) {
+        Objective o; check(lbfgsb200_objective_lennard_jones(device, epsilon, sigma, &o.h_));
+        if (fast) check(lbfgsb200_objective_set_lj_fast(o.h_, 1));
+        return o;
     }
     // kind 0 = Poisson (tests/owlqn.rs:22-43), 1 = logistic; X row-major nrow x ncol in device memory
     static Objective glm(int kind, const double *X_dev, const double *y_dev, int64_t nrow, int64_t ncol, int device = 0) {

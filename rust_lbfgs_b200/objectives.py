@@ -120,9 +120,15 @@ class Glm(_Builtin):
 class LennardJones(_Builtin):
     """examples/lj.rs:20-64,114-117: all-pairs LJ energy and gradient, x = 3 * atoms."""
 
-    def __init__(self, epsilon=1.0, sigma=1.0):
+    def __init__(self, epsilon=1.0, sigma=1.0, fast=False):
+        """fast=False: the reference's per-pair arithmetic (sqrt, divisions, powi: every pair term has the reference's
+        bits).  fast=True: the 1/r^2 molecular-dynamics form with fused multiply-adds — ~2.5x fewer FP64
+        instructions, pair terms within a few ulp (lbfgsb200_objective_set_lj_fast)."""
         super().__init__()
-        self.epsilon, self.sigma = float(epsilon), float(sigma)
+        self.epsilon, self.sigma, self.fast = float(epsilon), float(sigma), bool(fast)
 
     def _create(self, L, device, out):
-        return L.lbfgsb200_objective_lennard_jones(device, self.epsilon, self.sigma, C.byref(out))
+        st = L.lbfgsb200_objective_lennard_jones(device, self.epsilon, self.sigma, C.byref(out))
+        if st == 0 and self.fast:
+            st = L.lbfgsb200_objective_set_lj_fast(out, 1)
+        return st

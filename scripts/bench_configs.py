@@ -131,7 +131,10 @@ def cfg3(full):
 
 
 def cfg4(full):
-    """Lennard-Jones cluster on a jittered simple-cubic lattice (spacing 1.12, jitter 0.05, seed 7)."""
+    """Lennard-Jones cluster on a jittered simple-cubic lattice (spacing 1.12, jitter 0.05, seed 7).
+    LJ PARITY IS UNPINNED: the reference has no test for examples/lj.rs:20-64 (and its vecdist comes from the
+    un-vendored vecfx crate); the oracle restates it and the CUDA kernels are checked against that restatement only."""
+    import ctypes as C
     side = 47 if full else 16           # 47^3 = 103823 ~ 1e5 atoms
     rng = np.random.default_rng(7)
     g = np.arange(side, dtype=np.float64) * 1.12
@@ -139,18 +142,46 @@ def cfg4(full):
     p += rng.uniform(-0.05, 0.05, p.shape)
     na = p.shape[0]
     flat = p.ravel()
+    offs = None
+    if COMM is not None:   # atoms sharded: solver vectors and forces local, positions gathered per evaluation
+        offs = [D.shard_range(flat.size, r, WORLD, granule=6)[0] for r in range(WORLD)] + [flat.size]
+        x0 = torch.tensor(flat[offs[RANK]:offs[RANK + 1]], dtype=torch.float64, device=DEV)
+    else:
+        x0 = torch.tensor(flat, dtype=torch.float64, device=DEV)
+    # the objective alone, both per-pair arithmetics: ms per evaluation and ordered pairs per second
+    L = R.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    gx, fx = torch.empty_like(x0), torch.zeros(1, dtype=torch.float64, device=DEV)
+    for fast in (False, True):
+        lj = R.LennardJones(fast=fast)
+        if COMM is not None:
+            lj.shard(COMM, offs)
+        h = lj._user_ptr(LOCAL)
+        for _ in range(2):
+            L.lbfgsb200_objective_eval(h, x0.data_ptr(), gx.data_ptr(), x0.numel(), st, fx.data_ptr())
+        reps = 5
+        t0 = sync_time()
+        for _ in range(reps):
+            L.lbfgsb200_objective_eval(h, x0.data_ptr(), gx.data_ptr(), x0.numel(), st, fx.data_ptr())
+        t1 = sync_time()
+        if RANK == 0:
+            ms = 1e3 * (t1 - t0) / reps
+            print(json.dumps(dict(config=f"cfg4 lj objective alone, {na} atoms over {WORLD} GPU(s)",
+                                  arithmetic="1/r^2 + FMA (opt-in)" if fast else "reference per-pair arithmetic",
+                                  ms_per_evaluation=ms, ordered_pairs_per_s=na * (na - 1) / (ms / 1e3),
+                                  parity="UNPINNED (no reference test for examples/lj.rs; oracle restatement only)")), flush=True)
+        lj.close()
     for tag, mk in (("gradient-only max_linesearch=2", lambda: R.lbfgs().with_gradient_only().with_max_linesearch(2)),
                     ("damped", lambda: R.lbfgs().with_damping(True))):
-        b, lj = mk(), R.LennardJones()
-        if COMM is not None:   # atoms sharded: solver vectors and forces local, positions gathered per evaluation
-            offs = [D.shard_range(flat.size, r, WORLD, granule=6)[0] for r in range(WORLD)] + [flat.size]
-            lj.shard(COMM, offs)
-            b = b.with_shard(COMM, flat.size, offs[RANK])
-            x = torch.tensor(flat[offs[RANK]:offs[RANK + 1]], dtype=torch.float64, device=DEV)
-        else:
-            x = torch.tensor(flat, dtype=torch.float64, device=DEV)
-        solve(b, x, lj, f"cfg4 lj {na} atoms {tag}", extra=dict(pairs=na * (na - 1) // 2),
-              max_iter=21 if full else 41)
+        for fast in (False, True):
+            b, lj = mk(), R.LennardJones(fast=fast)
+            if COMM is not None:
+                lj.shard(COMM, offs)
+                b = b.with_shard(COMM, flat.size, offs[RANK])
+            x = x0.clone()
+            solve(b, x, lj, f"cfg4 lj {na} atoms {tag}" + (" [fast arithmetic]" if fast else ""),
+                  extra=dict(pairs=na * (na - 1) // 2, parity="UNPINNED"), max_iter=21 if full else 41)
+            lj.close()
 
 
 if __name__ == "__main__":

@@ -27,13 +27,15 @@ for n in (100, 1_000, 10_000, 100_000, 262_144, 300_000, 1_000_000):
         x[0::2], x[1::2] = -1.2, 1.0
         st = R.lbfgs().build(x, obj)
         st.profile_enable(True)
-        for _ in range(ITERS + 1):
+        done = 0
+        while done < ITERS + 1 and not st.is_converged():
             st.propagate()
+            done += 1
         p = st.profile()
         st.close()
         upd = sum(p["ms"][k] for k in ("history", "commit", "damp", "backward", "forward", "update_small"))
         ls = sum(p["ms"][k] for k in ("probe", "trial_eval", "trial", "evaluate", "dots"))
         print(f"n={n} two_loop={'cluster kernel' if small == '1' and p['launches']['update_small'] else 'kernel chain'}: "
               f"{1e6 * best / ITERS:.1f} us/iteration ({r.neval} evaluations); kernel time per iteration: update "
-              f"{1e3 * upd / ITERS:.1f} us, line search {1e3 * ls / ITERS:.1f} us", flush=True)
+              f"{1e3 * upd / max(1, done - 1):.1f} us, line search {1e3 * ls / max(1, done - 1):.1f} us", flush=True)
 os.environ.pop("LBFGSB200_SMALL", None)

@@ -193,11 +193,28 @@ def test_objectives_match_oracle(oracle, golden_dir):
     assert f == fr and np.array_equal(g, gr)
 
     p = np.load(os.path.join(golden_dir, "lj38.npy")).ravel().copy()
-    f, g = run(R.LennardJones(), p)
     gr = np.zeros_like(p)
     fr = O.oracle_eval_lj(None, p.ctypes.data, gr.ctypes.data, p.size, C.byref(err))
-    assert np.array_equal(g, gr)                 # ascending-partner accumulation order == the reference's
-    assert abs(f - fr) <= 1e-13 * abs(fr)
+    lj = R.LennardJones()
+    lj._set_reduction(0, R._lib.REDUCE_SEQUENTIAL)
+    f, g = run(lj, p)
+    assert np.array_equal(g, gr) and f == fr     # one thread per atom, ascending partners == the reference's order
+    lj._set_reduction(0, R._lib.REDUCE_TREE)
+    f, g = run(lj, p)                            # production: lanes per atom, the reference's per-pair arithmetic
+    assert np.max(np.abs(g - gr)) <= 1e-14 * np.max(np.abs(gr)) and abs(f - fr) <= 1e-13 * abs(fr)
+    f, g = run(R.LennardJones(fast=True), p)     # opt-in: 1/r^2 formulation, fused multiply-adds
+    assert np.max(np.abs(g - gr)) <= 1e-13 * np.max(np.abs(gr)) and abs(f - fr) <= 1e-13 * abs(fr)
+    # a larger jittered lattice (the shape of BASELINE configs[3]): both arithmetics against the oracle
+    rng = np.random.default_rng(7)
+    side = 12
+    grid3 = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), -1).reshape(-1, 3) * 1.12
+    p = (grid3 + rng.uniform(-0.05, 0.05, grid3.shape)).ravel()
+    gr = np.zeros_like(p)
+    fr = O.oracle_eval_lj(None, p.ctypes.data, gr.ctypes.data, p.size, C.byref(err))
+    for fast, tol in ((False, 1e-14), (True, 1e-13)):
+        f, g = run(R.LennardJones(fast=fast), p)
+        assert np.max(np.abs(g - gr)) <= tol * np.max(np.abs(gr)), (fast, np.max(np.abs(g - gr)) / np.max(np.abs(gr)))
+        assert abs(f - fr) <= 1e-12 * abs(fr), (fast, f, fr)
 
     d = np.load(os.path.join(golden_dir, "poisson_500x21.npz"))
     X, y = d["X"], d["y"]
