@@ -370,6 +370,16 @@ int  lbfgsb200_objective_glm(int device, int kind, const double *X_dev, const do
                              int64_t ncol, lbfgsb200_objective_t **out);
 /* all-pairs Lennard-Jones  examples/lj.rs:20-64,114-117; n = 3 * atoms */
 int  lbfgsb200_objective_lennard_jones(int device, double epsilon, double sigma, lbfgsb200_objective_t **out);
+/* Which kernels the last GLM evaluation ran (diagnostic; 0 before the first one): the one-pass kernel covers even
+ * ncol up to 10 240 per CTA, odd ncol up to 6 143 (rows only 8-byte aligned), and even ncol up to 163 840 with the
+ * columns split over a thread-block cluster; anything else takes the two-pass kernels (X read twice). */
+enum {
+    LBFGSB200_GLM_PATH_TWO_PASS = 1,
+    LBFGSB200_GLM_PATH_FUSED = 2,
+    LBFGSB200_GLM_PATH_FUSED_ODD = 3,
+    LBFGSB200_GLM_PATH_FUSED_CLUSTER = 4
+};
+int  lbfgsb200_objective_last_path(const lbfgsb200_objective_t *objective);
 /* Lennard-Jones per-pair arithmetic.  0 (default): the reference's — sqrt, sigma/r, powi, g*dr/r with IEEE
  * divisions (examples/lj.rs:23-32,50-57), so every pair term has the reference's bits.  1: the molecular-dynamics
  * form — only 1/r^2 (reciprocal seed + two Newton steps), fused multiply-adds; ~2.5x fewer FP64 instructions,

@@ -27,6 +27,7 @@ REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
 ABI_VERSION = 3
 FUSED_SUMS_OVER_RANKS = 1
 FUSED_COMMIT_SKIPS_GP = 2
+GLM_PATH_TWO_PASS, GLM_PATH_FUSED, GLM_PATH_FUSED_ODD, GLM_PATH_FUSED_CLUSTER = 1, 2, 3, 4
 LS_MORETHUENTE, LS_BACKTRACKING_ARMIJO, LS_BACKTRACKING_WOLFE, LS_BACKTRACKING_STRONG_WOLFE = 0, 1, 2, 3
 UNIQUE_ID_BYTES = 128
 
@@ -166,6 +167,7 @@ def lib():
     _sig(L, "lbfgsb200_objective_lennard_jones", i32, [i32, dbl, dbl, pp(vp)])
     _sig(L, "lbfgsb200_objective_set_reduction", i32, [vp, i32])
     _sig(L, "lbfgsb200_objective_set_lj_fast", i32, [vp, i32])
+    _sig(L, "lbfgsb200_objective_last_path", i32, [vp])
     _sig(L, "lbfgsb200_objective_set_shard", i32, [vp, vp, pp(i64)])
     _sig(L, "lbfgsb200_objective_has_trial_eval", i32, [vp])
     _sig(L, "lbfgsb200_objective_trial_eval", i32, [vp, vp, vp, dbl, vp, vp, i64, vp, vp])

@@ -7,6 +7,7 @@
 //   GLM            tests/owlqn.rs:22-43 (Poisson) + logistic       (dense X in HBM)
 //   Lennard-Jones  examples/lj.rs:20-64,114-117                    (all pairs, FP64)
 // Element-wise arithmetic keeps the reference's operation order (-fmad=false).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -38,6 +39,7 @@ struct Objective {
     int row_chunks = 0;
     double *gfused = nullptr;    // [sm_count][ncol] per-CTA partial gradients of the fused one-pass kernel
     bool fused = true;           // LBFGSB200_GLM_FUSED=0 forces the two-pass kernels
+    int last_path = 0;           // which kernels the last GLM evaluation used (lbfgsb200_objective_last_path)
     // LJ
     double eps = 1.0, sigma = 1.0;
     bool lj_fast = false;        // lj_pair_fast instead of the reference's per-pair arithmetic (opt-in)
@@ -261,9 +263,8 @@ __global__ void __launch_bounds__(kThreads) k_glm_grad_final(const double *__res
 // ---- GLM, fused: ONE pass over X ---------------------------------------------------------------------
 // z_r = X[r,:].w, the per-row loss term and residual t_r, and the gradient update g += t_r X[r,:] all while
 // row r is on chip, so X (80 GB at 1e6 x 1e4) crosses HBM once per evaluation instead of twice.
-//   * one 256-thread CTA per SM owns row groups g = blockIdx.x, + gridDim.x, ... of R consecutive rows
-//     (R = 1 for 80 KB rows, up to 8 for short ones: ~64 KB per group, so the two block barriers per group
-//     are amortised);
+//   * one 256-thread CTA per SM owns row groups of R consecutive rows (R = 1 for 80 KB rows, up to 8 for short
+//     ones: ~64 KB per group, so the two block barriers per group are amortised);
 //   * groups are staged in shared memory by 1-D TMA bulk copies (cp.async.bulk -> mbarrier complete_tx), a ring
 //     of `stages` buffers so the next groups are in flight while this one is consumed (2 stages of 80 KB at
 //     ncol = 1e4, more for shorter rows);
@@ -271,7 +272,13 @@ __global__ void __launch_bounds__(kThreads) k_glm_grad_final(const double *__res
 //     registers for the whole kernel; the row is read from shared memory twice (dot, then axpy);
 //   * per-CTA partial gradients go to gpart[cta][ncol] and are summed in CTA order by k_glm_grad_final;
 //     f goes through the usual deterministic two-level reduction.
-// Requires ncol even (16-byte aligned rows) and ncol <= 512 * KP; other shapes use the two-pass kernels above.
+// ODD (ncol odd, e.g. the reference's 500 x 21 fixture): rows are only 8-byte aligned, so R is even (every group
+// starts 16-byte aligned), elements are read from shared memory as scalars and the odd 8 bytes a short last group
+// may leave are copied by hand.
+// CLUSTER (ncol > 10 240: a row no longer fits one CTA's registers / shared memory): the C CTAs of a thread-block
+// cluster split the COLUMNS of the same rows; each stages and keeps its slice, the partial dot products z_r meet
+// through distributed shared memory (one hardware cluster barrier per row, summed in rank order by every CTA),
+// and each CTA updates its own slice of the gradient.  Still one pass over X.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -303,43 +310,68 @@ constexpr uint32_t kTmaChunk = 32768;  // bytes per bulk copy
 // pay two block barriers each — a 16 KB row lasts 0.36 us at this SM's share of the HBM bandwidth — so a stage
 // holds R rows (they are contiguous in X: one bulk copy), the R dot products are reduced together and the R
 // rank-one updates applied together.
-template <int KP, int R>
+template <int KP, int R, bool ODD, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const double *__restrict__ w,
             double *__restrict__ gpart, int64_t nrow, int64_t ncol, int kind, int stages, uint32_t stage_stride,
             ReduceWs ws, double *fx) {
+    static_assert(!(ODD && CLUSTER), "the column-split kernel takes even ncol only");
+    static_assert(!CLUSTER || R == 1, "column split: one row per stage");
     extern __shared__ __align__(128) unsigned char glm_smem[];
     __shared__ __align__(8) uint64_t full_bar[kGlmMaxStages];
     __shared__ double red[2][R][kWarps];
+    __shared__ double zcta[2][R];                    // CLUSTER: this CTA's partial dot products, read by its peers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t npairs = ncol >> 1;
-    const uint32_t row_bytes = (uint32_t)(ncol * 8);
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int csize = CLUSTER ? (int)cluster.num_blocks() : 1;
+    const int crank = CLUSTER ? (int)cluster.block_rank() : 0;
+    const int64_t cid = blockIdx.x / csize;          // which row-group stream this CTA (cluster) walks
+    const int64_t ncl = gridDim.x / csize;
+    const int64_t npairs_all = (ncol + 1) >> 1;      // ODD: the last pair has one element
+    // this CTA's columns: pairs [p0, p1)
+    const int64_t chunk = (npairs_all + csize - 1) / csize;
+    const int64_t p0 = (int64_t)crank * chunk;
+    const int64_t p1 = (p0 + chunk < npairs_all) ? (p0 + chunk) : npairs_all;
+    const uint32_t row_bytes = (uint32_t)(ncol * 8);                 // a full row of X
+    const uint32_t slice_bytes = CLUSTER ? (uint32_t)((p1 > p0 ? p1 - p0 : 0) * 16) : row_bytes;   // what this CTA stages per row
     const int64_t ngroups = (nrow + R - 1) / R;      // groups of R rows; the last one may be short
-    const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_groups = (ngroups > cid) ? (ngroups - cid + ncl - 1) / ncl : 0;
 
     double2 wv[KP], gv[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        const int64_t p = tid + (int64_t)k * kThreads;
-        wv[k] = (p < npairs) ? reinterpret_cast<const double2 *>(w)[p] : make_double2(0.0, 0.0);
+        const int64_t p = p0 + tid + (int64_t)k * kThreads;
+        wv[k] = make_double2(0.0, 0.0);
+        if (p < p1) {
+            if (ODD) {
+                wv[k].x = w[2 * p];
+                if (2 * p + 1 < ncol) wv[k].y = w[2 * p + 1];
+            } else {
+                wv[k] = reinterpret_cast<const double2 *>(w)[p];
+            }
+        }
         gv[k] = make_double2(0.0, 0.0);
     }
     auto rows_in = [&](int64_t i) {  // rows of this CTA's i-th group
-        const int64_t r0 = (blockIdx.x + i * gridDim.x) * R;
+        const int64_t r0 = (cid + i * ncl) * R;
         return (int)((nrow - r0 < R) ? (nrow - r0) : R);
     };
     auto issue = [&](int64_t i) {  // thread 0: stage group i of this CTA
         const int s = (int)(i % stages);
-        const int64_t r0 = (blockIdx.x + i * gridDim.x) * R;
-        const uint32_t bytes = row_bytes * (uint32_t)rows_in(i);
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(X + r0 * ncol);
+        const int64_t r0 = (cid + i * ncl) * R;
+        const uint32_t bytes = CLUSTER ? slice_bytes : row_bytes * (uint32_t)rows_in(i);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(X + r0 * ncol) + (CLUSTER ? p0 * 16 : 0);
         unsigned char *dst = glm_smem + (size_t)s * stage_stride;
+        const uint32_t bulk = ODD ? (bytes & ~15u) : bytes;           // ODD: a short last group may end on 8 bytes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this buffer
-        mbar_expect_tx(&full_bar[s], bytes);
-        for (uint32_t off = 0; off < bytes; off += kTmaChunk) {
-            const uint32_t nb = (bytes - off < kTmaChunk) ? (bytes - off) : kTmaChunk;
+        mbar_expect_tx(&full_bar[s], bulk);
+        for (uint32_t off = 0; off < bulk; off += kTmaChunk) {
+            const uint32_t nb = (bulk - off < kTmaChunk) ? (bulk - off) : kTmaChunk;
             tma_load_1d(dst + off, src + off, nb, &full_bar[s]);
         }
+        if (ODD && bulk != bytes)   // consumers see it through the block barriers between here and their reads
+            *reinterpret_cast<double *>(dst + bulk) = *reinterpret_cast<const double *>(src + bulk);
     };
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
@@ -348,11 +380,19 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
     __syncthreads();
     if (tid == 0)
         for (int64_t i = 0; i < stages && i < my_groups; ++i) issue(i);
+    if (ODD) __syncthreads();   // the hand-copied tail of a prologue group
 
     double facc = 0.0;   // lanes 0..R-1 of warp 0 accumulate the loss terms of "their" row of every group
     auto load_y = [&](int64_t i) {
-        const int64_t r = (blockIdx.x + i * gridDim.x) * R + lane;
+        const int64_t r = (cid + i * ncl) * R + lane;
         return (lane < R && i < my_groups && r < nrow) ? y[r] : 0.0;
+    };
+    auto row_pair = [&](const unsigned char *stage, int r, int64_t p) {   // pair p of row r of a staged group
+        if (ODD) {
+            const double *row = reinterpret_cast<const double *>(stage + (size_t)r * row_bytes);
+            return make_double2(row[2 * p], (2 * p + 1 < ncol) ? row[2 * p + 1] : 0.0);
+        }
+        return reinterpret_cast<const double2 *>(stage + (size_t)r * (CLUSTER ? slice_bytes : row_bytes))[p - p0];
     };
     double y_next = load_y(0);
     for (int64_t i = 0; i < my_groups; ++i) {
@@ -368,12 +408,12 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
         for (int r = 0; r < R; ++r) part[r] = 0.0;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            const int64_t p = tid + (int64_t)k * kThreads;
-            if (p < npairs) {
+            const int64_t p = p0 + tid + (int64_t)k * kThreads;
+            if (p < p1) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (r < nr) {
-                        const double2 xv = reinterpret_cast<const double2 *>(stage + (size_t)r * row_bytes)[p];
+                        const double2 xv = row_pair(stage, r, p);
                         part[r] += wv[k].x * xv.x;
                         part[r] += wv[k].y * xv.y;
                     }
@@ -386,12 +426,28 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
             if (lane == 0) red[i & 1][r][warp] = v;
         }
         __syncthreads();
+        if (CLUSTER) {   // this CTA's partial z, then the peers' through DSMEM
+            if (tid < nr) {
+                double zc = 0.0;
+#pragma unroll
+                for (int q = 0; q < kWarps; ++q) zc += red[i & 1][tid][q];
+                zcta[i & 1][tid] = zc;
+            }
+            cluster.sync();
+        }
         // lane r of every warp finishes row r: z, the link function, t; warp 0 also books the loss term
         double t_mine = 0.0;
         if (lane < nr) {
             double z = 0.0;
+            if (CLUSTER) {
+                for (int rk = 0; rk < csize; ++rk) {   // fixed rank order: the same z in every CTA of the cluster
+                    const double(*peer)[R] = cluster.map_shared_rank(zcta, rk);
+                    z += peer[i & 1][lane];
+                }
+            } else {
 #pragma unroll
-            for (int q = 0; q < kWarps; ++q) z += red[i & 1][lane][q];
+                for (int q = 0; q < kWarps; ++q) z += red[i & 1][lane][q];
+            }
             double term;
             if (kind == 0) {
                 const double e = exp(z);
@@ -405,19 +461,19 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
                 term = sp - yr * z;
                 t_mine = mu - yr;
             }
-            if (warp == 0) facc += term;
+            if (warp == 0 && crank == 0) facc += term;    // one CTA of a cluster books the row's loss term
         }
         double t[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) t[r] = __shfl_sync(0xffffffffu, t_mine, r);
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            const int64_t p = tid + (int64_t)k * kThreads;
-            if (p < npairs) {
+            const int64_t p = p0 + tid + (int64_t)k * kThreads;
+            if (p < p1) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (r < nr) {
-                        const double2 xv = reinterpret_cast<const double2 *>(stage + (size_t)r * row_bytes)[p];
+                        const double2 xv = row_pair(stage, r, p);
                         gv[k].x += t[r] * xv.x;
                         gv[k].y += t[r] * xv.y;
                     }
@@ -427,17 +483,39 @@ k_glm_fused(const double *__restrict__ X, const double *__restrict__ y, const do
         __syncthreads();  // every thread is done with stage s: it may be refilled
         if (tid == 0 && i + stages < my_groups) issue(i + stages);
     }
-    double *gp = gpart + (int64_t)blockIdx.x * ncol;
+    double *gp = gpart + cid * ncol;
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        const int64_t p = tid + (int64_t)k * kThreads;
-        if (p < npairs) reinterpret_cast<double2 *>(gp)[p] = gv[k];
+        const int64_t p = p0 + tid + (int64_t)k * kThreads;
+        if (p < p1) {
+            if (ODD) {
+                gp[2 * p] = gv[k].x;
+                if (2 * p + 1 < ncol) gp[2 * p + 1] = gv[k].y;
+            } else {
+                reinterpret_cast<double2 *>(gp)[p] = gv[k];
+            }
+        }
     }
     double acc[1] = {(kind == 0) ? -1.0 * facc : facc};
     grid_reduce<1>(acc, ws, fx);
+    if (CLUSTER) cluster.sync();   // no CTA exits while a peer may still read its zcta
 }
 
-template <int KP, int R>
+// function attributes are per device: one opt-in per (instantiation, device)
+template <int KP, int R, bool ODD, bool CLUSTER>
+bool glm_fused_attrs(int device, bool nonportable) {
+    static bool attr_set[64] = {};
+    if (device >= 0 && device < 64 && attr_set[device]) return true;
+    if (cudaFuncSetAttribute(k_glm_fused<KP, R, ODD, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        (nonportable && cudaFuncSetAttribute(k_glm_fused<KP, R, ODD, CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+        cudaGetLastError();
+        return false;
+    }
+    if (device >= 0 && device < 64) attr_set[device] = true;
+    return true;
+}
+
+template <int KP, int R, bool ODD>
 int launch_glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
     const uint32_t row_bytes = (uint32_t)(o->ncol * 8);
     const uint32_t stage_stride = (row_bytes * (uint32_t)R + 127u) & ~127u;
@@ -445,48 +523,83 @@ int launch_glm_fused(Objective *o, const double *w, double *g, cudaStream_t stre
     if (stages > kGlmMaxStages) stages = kGlmMaxStages;
     if (stages < 2) return LBFGSB200_ERR_UNSUPPORTED;
     const size_t smem = (size_t)stages * stage_stride;
-    static bool attr_set[64] = {};   // function attributes are per device: one opt-in per (instantiation, device)
-    const int di = o->dev.device;
-    if (di < 0 || di >= 64 || !attr_set[di]) {
-        if (cudaFuncSetAttribute(k_glm_fused<KP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-            cudaGetLastError();
-            return LBFGSB200_ERR_UNSUPPORTED;   // the caller falls back to the two-pass kernels
-        }
-        if (di >= 0 && di < 64) attr_set[di] = true;
-    }
+    if (!glm_fused_attrs<KP, R, ODD, false>(o->dev.device, false)) return LBFGSB200_ERR_UNSUPPORTED;   // two-pass kernels instead
     const int64_t ngroups = (o->nrow + R - 1) / R;
     int grid = o->dev.sm_count;
     if ((int64_t)grid > ngroups) grid = (int)ngroups;
-    k_glm_fused<KP, R><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind, stages,
-                                                          stage_stride, o->ws, fx);
+    k_glm_fused<KP, R, ODD, false><<<grid, kThreads, smem, stream>>>(o->X, o->y, w, o->gfused, o->nrow, o->ncol, o->glm_kind,
+                                                                      stages, stage_stride, o->ws, fx);
     if (cudaGetLastError() != cudaSuccess) return LBFGSB200_ERR_UNSUPPORTED;   // launch refused: two-pass kernels instead
     const unsigned cb = (unsigned)((o->ncol + kThreads - 1) / kThreads);
     k_glm_grad_final<<<cb, kThreads, 0, stream>>>(o->gfused, g, o->ncol, grid);
     return 0;
 }
 
+// ncol > 10 240 (even): C CTAs of a cluster split the columns, KP = 20 pairs per thread each.
+int launch_glm_fused_cluster(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
+    const int64_t npairs = o->ncol / 2;
+    int c = 2;
+    while (c < 16 && (npairs + c - 1) / c > 20 * kThreads) c *= 2;
+    if ((npairs + c - 1) / c > 20 * kThreads) return LBFGSB200_ERR_UNSUPPORTED;
+    const uint32_t slice = (uint32_t)(((npairs + c - 1) / c) * 16);
+    const uint32_t stage_stride = (slice + 127u) & ~127u;
+    int stages = (int)((200u * 1024u) / stage_stride);
+    if (stages > kGlmMaxStages) stages = kGlmMaxStages;
+    if (stages < 2) return LBFGSB200_ERR_UNSUPPORTED;
+    if (!glm_fused_attrs<20, 1, false, true>(o->dev.device, c > 8)) return LBFGSB200_ERR_UNSUPPORTED;
+    int nclusters = o->dev.sm_count / c;
+    if ((int64_t)nclusters > o->nrow) nclusters = (int)o->nrow;
+    if (nclusters < 1) return LBFGSB200_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nclusters * c));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)stages * stage_stride;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)c;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_glm_fused<20, 1, false, true>, o->X, o->y, w, o->gfused, o->nrow, o->ncol,
+                                             o->glm_kind, stages, stage_stride, o->ws, fx);
+    if (e != cudaSuccess) { cudaGetLastError(); return LBFGSB200_ERR_UNSUPPORTED; }
+    const unsigned cb = (unsigned)((o->ncol + kThreads - 1) / kThreads);
+    k_glm_grad_final<<<cb, kThreads, 0, stream>>>(o->gfused, g, o->ncol, nclusters);
+    return 0;
+}
+
 // rows per stage: enough for ~32-64 KB per stage (R * 16 B-aligned rows are contiguous in X)
-template <int KP>
+template <int KP, bool ODD>
 int launch_glm_fused_r(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
     const int64_t row_bytes = o->ncol * 8;
-    if (row_bytes * 8 <= 65536) return launch_glm_fused<KP, 8>(o, w, g, stream, fx);
-    if (row_bytes * 4 <= 65536) return launch_glm_fused<KP, 4>(o, w, g, stream, fx);
-    if (row_bytes * 2 <= 65536) return launch_glm_fused<KP, 2>(o, w, g, stream, fx);
-    return launch_glm_fused<KP, 1>(o, w, g, stream, fx);
+    if (row_bytes * 8 <= 65536) return launch_glm_fused<KP, 8, ODD>(o, w, g, stream, fx);
+    if (row_bytes * 4 <= 65536) return launch_glm_fused<KP, 4, ODD>(o, w, g, stream, fx);
+    if (row_bytes * 2 <= 65536 || ODD) return launch_glm_fused<KP, 2, ODD>(o, w, g, stream, fx);   // ODD: R stays even
+    return launch_glm_fused<KP, 1, false>(o, w, g, stream, fx);
 }
 
 // 0 = launched; LBFGSB200_ERR_UNSUPPORTED = shape not covered (caller falls back to the two-pass kernels)
 int glm_fused(Objective *o, const double *w, double *g, cudaStream_t stream, double *fx) {
-    if (!o->gfused || (o->ncol & 1) || (((uintptr_t)o->X | (uintptr_t)w) & 15u)) return LBFGSB200_ERR_UNSUPPORTED;
-    const int64_t need = (o->ncol / 2 + kThreads - 1) / kThreads;  // column pairs per thread
-    if (need <= 1) return launch_glm_fused_r<1>(o, w, g, stream, fx);
-    if (need <= 2) return launch_glm_fused_r<2>(o, w, g, stream, fx);
-    if (need <= 4) return launch_glm_fused_r<4>(o, w, g, stream, fx);
-    if (need <= 8) return launch_glm_fused_r<8>(o, w, g, stream, fx);
-    if (need <= 12) return launch_glm_fused<12, 1>(o, w, g, stream, fx);
-    if (need <= 16) return launch_glm_fused<16, 1>(o, w, g, stream, fx);
-    if (need <= 20) return launch_glm_fused<20, 1>(o, w, g, stream, fx);
-    return LBFGSB200_ERR_UNSUPPORTED;
+    if (!o->gfused || (((uintptr_t)o->X | (uintptr_t)w) & 15u)) return LBFGSB200_ERR_UNSUPPORTED;
+    const int64_t need = ((o->ncol + 1) / 2 + kThreads - 1) / kThreads;  // column pairs per thread
+    if (o->ncol & 1) {   // odd ncol: scalar shared-memory reads, even R
+        if (need <= 1) return launch_glm_fused_r<1, true>(o, w, g, stream, fx);
+        if (need <= 2) return launch_glm_fused_r<2, true>(o, w, g, stream, fx);
+        if (need <= 4) return launch_glm_fused_r<4, true>(o, w, g, stream, fx);
+        if (need <= 8) return launch_glm_fused_r<8, true>(o, w, g, stream, fx);
+        if (need <= 12) return launch_glm_fused<12, 2, true>(o, w, g, stream, fx);   // up to ncol = 6 143
+        return LBFGSB200_ERR_UNSUPPORTED;
+    }
+    if (need <= 1) return launch_glm_fused_r<1, false>(o, w, g, stream, fx);
+    if (need <= 2) return launch_glm_fused_r<2, false>(o, w, g, stream, fx);
+    if (need <= 4) return launch_glm_fused_r<4, false>(o, w, g, stream, fx);
+    if (need <= 8) return launch_glm_fused_r<8, false>(o, w, g, stream, fx);
+    if (need <= 12) return launch_glm_fused<12, 1, false>(o, w, g, stream, fx);
+    if (need <= 16) return launch_glm_fused<16, 1, false>(o, w, g, stream, fx);
+    if (need <= 20) return launch_glm_fused<20, 1, false>(o, w, g, stream, fx);
+    return launch_glm_fused_cluster(o, w, g, stream, fx);   // ncol > 10 240: columns split over a CTA cluster
 }
 
 // ---- Lennard-Jones: all pairs, FP64-pipe bound -------------------------------------------------------------
@@ -793,9 +906,14 @@ int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t 
             if (n != o->ncol) return LBFGSB200_ERR_INVALID_PARAM;
             if (o->fused) {
                 const int frc = glm_fused(o, x, g, stream, fx);
-                if (frc == 0) break;
+                if (frc == 0) {
+                    o->last_path = (o->ncol & 1) ? LBFGSB200_GLM_PATH_FUSED_ODD
+                                                 : (o->ncol > 20 * 2 * kThreads ? LBFGSB200_GLM_PATH_FUSED_CLUSTER : LBFGSB200_GLM_PATH_FUSED);
+                    break;
+                }
                 if (frc != LBFGSB200_ERR_UNSUPPORTED) return frc;
             }
+            o->last_path = LBFGSB200_GLM_PATH_TWO_PASS;
             int64_t blocks = (o->nrow + kWarps - 1) / kWarps;
             const int64_t cap = (int64_t)o->dev.sm_count * 8;
             if (blocks > cap) blocks = cap;
@@ -907,6 +1025,10 @@ int lbfgsb200_objective_set_reduction(lbfgsb200_objective_t *objective, int redu
     if (reduction == LBFGSB200_REDUCE_SEQUENTIAL && o->kind == lb::OBJ_GLM) return LBFGSB200_ERR_UNSUPPORTED;
     o->sequential = reduction == LBFGSB200_REDUCE_SEQUENTIAL;
     return 0;
+}
+int lbfgsb200_objective_last_path(const lbfgsb200_objective_t *objective) {
+    const lb::Objective *o = reinterpret_cast<const lb::Objective *>(objective);
+    return o ? o->last_path : 0;
 }
 int lbfgsb200_objective_set_lj_fast(lbfgsb200_objective_t *objective, int fast) {
     lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);

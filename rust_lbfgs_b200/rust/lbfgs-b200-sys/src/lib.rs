@@ -1,8 +1,8 @@
-//! Raw bindings to `include/lbfgsb200.h` (ABI version 2).  One item per C declaration, same order.
+//! Raw bindings to `include/lbfgsb200.h` (ABI version 3).  One item per C declaration, same order.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const LBFGSB200_ABI_VERSION: c_int = 2;
+pub const LBFGSB200_ABI_VERSION: c_int = 3;
 
 pub const LBFGSB200_OK_CONVERGED: c_int = 0;
 pub const LBFGSB200_OK_MAX_ITERATIONS: c_int = 1;
@@ -86,7 +86,7 @@ pub struct lbfgsb200_report_t {
     pub status: i64,
 }
 
-pub const LBFGSB200_K_COUNT: usize = 12;
+pub const LBFGSB200_K_COUNT: usize = 15;
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
 pub struct lbfgsb200_profile_t {
@@ -106,6 +106,36 @@ pub type lbfgsb200_eval_fn = Option<unsafe extern "C" fn(user: *mut c_void, x_de
     n_local: i64, stream: *mut c_void, fx_dev: *mut f64) -> c_int>;
 pub type lbfgsb200_trial_eval_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
     step: f64, x_dev: *mut f64, g_dev: *mut f64, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
+pub type lbfgsb200_probe_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64,
+    n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
+pub type lbfgsb200_commit_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
+    gp_dev: *const f64, step: f64, bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
+    n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
+
+pub const LBFGSB200_FUSED_SUMS_OVER_RANKS: i64 = 1;
+pub const LBFGSB200_FUSED_COMMIT_SKIPS_GP: i64 = 2;
+/// `lbfgsb200_fused_ops_t`: what an objective offers beyond evaluate.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct lbfgsb200_fused_ops_t {
+    pub struct_size: i64,
+    pub trial: lbfgsb200_trial_eval_fn,
+    pub probe: lbfgsb200_probe_fn,
+    pub commit: lbfgsb200_commit_fn,
+    pub user: *mut c_void,
+    pub flags: i64,
+}
+impl Default for lbfgsb200_fused_ops_t {
+    fn default() -> Self {
+        Self { struct_size: std::mem::size_of::<Self>() as i64, trial: None, probe: None, commit: None, user: std::ptr::null_mut(), flags: 0 }
+    }
+}
+
+pub const LBFGSB200_GLM_PATH_TWO_PASS: c_int = 1;
+pub const LBFGSB200_GLM_PATH_FUSED: c_int = 2;
+pub const LBFGSB200_GLM_PATH_FUSED_ODD: c_int = 3;
+pub const LBFGSB200_GLM_PATH_FUSED_CLUSTER: c_int = 4;
+
 pub type lbfgsb200_progress_fn = Option<unsafe extern "C" fn(user: *mut c_void, progress: *const lbfgsb200_progress_t) -> c_int>;
 
 extern "C" {
@@ -125,6 +155,7 @@ extern "C" {
     pub fn lbfgsb200_minimize(solver: *mut lbfgsb200_solver_t, x_dev: *mut f64, eval: lbfgsb200_eval_fn, eval_user: *mut c_void,
                               progress: lbfgsb200_progress_fn, progress_user: *mut c_void, report: *mut lbfgsb200_report_t) -> c_int;
     pub fn lbfgsb200_set_trial_evaluate(solver: *mut lbfgsb200_solver_t, f: lbfgsb200_trial_eval_fn, user: *mut c_void) -> c_int;
+    pub fn lbfgsb200_set_fused_ops(solver: *mut lbfgsb200_solver_t, ops: *const lbfgsb200_fused_ops_t) -> c_int;
     pub fn lbfgsb200_build(solver: *mut lbfgsb200_solver_t, x_dev: *mut f64, eval: lbfgsb200_eval_fn, eval_user: *mut c_void) -> c_int;
     pub fn lbfgsb200_is_converged(solver: *mut lbfgsb200_solver_t, stop_status: *mut c_int) -> c_int;
     pub fn lbfgsb200_propagate(solver: *mut lbfgsb200_solver_t, progress_out: *mut lbfgsb200_progress_t) -> c_int;
@@ -139,7 +170,7 @@ extern "C" {
 
     pub fn lbfgsb200_minimize_host_ex(param: *const lbfgsb200_param_t, x_host: *mut f64, n_local: i64, n_global: i64, global_offset: i64,
                                       device: c_int, comm: *mut lbfgsb200_comm_t, eval: lbfgsb200_eval_fn, eval_user: *mut c_void,
-                                      trial_eval: lbfgsb200_trial_eval_fn, trial_user: *mut c_void, progress: lbfgsb200_progress_fn,
+                                      fused: *const lbfgsb200_fused_ops_t, progress: lbfgsb200_progress_fn,
                                       progress_user: *mut c_void, report: *mut lbfgsb200_report_t) -> c_int;
     pub fn lbfgsb200_profile_enable(solver: *mut lbfgsb200_solver_t, timing: c_int) -> c_int;
     pub fn lbfgsb200_profile_get(solver: *mut lbfgsb200_solver_t, out: *mut lbfgsb200_profile_t) -> c_int;
@@ -164,6 +195,19 @@ extern "C" {
     pub fn lbfgsb200_owl_constrain_direction(d_dev: *mut f64, pg_dev: *const f64, n: i64, start: i64, end: i64, stream: *mut c_void,
                                              out_host: *mut f64) -> c_int;
 
+    // the update chain's kernels, one call each (scalars by value)
+    pub fn lbfgsb200_init_direction(d_dev: *mut f64, g_dev: *const f64, n: i64, stream: *mut c_void, out_host: *mut f64) -> c_int;
+    pub fn lbfgsb200_history_update(s_dev: *mut f64, y_dev: *mut f64, x_dev: *const f64, xp_dev: *const f64, g_dev: *const f64,
+                                    gp_dev: *const f64, pg_dev: *const f64, n: i64, step: f64, damping: c_int, stream: *mut c_void,
+                                    out_host: *mut f64) -> c_int;
+    pub fn lbfgsb200_damp_y(y_dev: *mut f64, gp_dev: *const f64, n: i64, step: f64, ys: f64, sbs: f64, stream: *mut c_void,
+                            applied_host: *mut c_int) -> c_int;
+    pub fn lbfgsb200_two_loop_backward_step(q_dev: *mut f64, g_first_dev: *const f64, y_j_dev: *const f64, s_next_dev: *const f64,
+                                            n: i64, sq: f64, ys_j: f64, gamma: f64, stream: *mut c_void, out_host: *mut f64) -> c_int;
+    pub fn lbfgsb200_two_loop_forward_step(r_dev: *mut f64, s_j_dev: *const f64, y_next_dev: *const f64, g_last_dev: *const f64,
+                                           n: i64, yr: f64, ys_j: f64, alpha_j: f64, owl: c_int, owl_start: i64, owl_end: i64,
+                                           stream: *mut c_void, out_host: *mut f64) -> c_int;
+
     pub fn lbfgsb200_objective_rosenbrock(device: c_int, out: *mut *mut lbfgsb200_objective_t) -> c_int;
     pub fn lbfgsb200_objective_booth(device: c_int, out: *mut *mut lbfgsb200_objective_t) -> c_int;
     pub fn lbfgsb200_objective_glm(device: c_int, kind: c_int, x_dev: *const f64, y_dev: *const f64, nrow: i64, ncol: i64,
@@ -177,6 +221,14 @@ extern "C" {
     pub fn lbfgsb200_objective_trial_eval(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64, x_dev: *mut f64,
                                           g_dev: *mut f64, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
     pub fn lbfgsb200_objective_has_trial_eval(objective: *const lbfgsb200_objective_t) -> c_int;
+    pub fn lbfgsb200_objective_probe(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64, n_local: i64,
+                                     stream: *mut c_void, out_dev: *mut f64) -> c_int;
+    pub fn lbfgsb200_objective_commit(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
+                                      bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
+                                      n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
+    pub fn lbfgsb200_objective_fused_ops(objective: *mut lbfgsb200_objective_t, out: *mut lbfgsb200_fused_ops_t) -> c_int;
+    pub fn lbfgsb200_objective_last_path(objective: *const lbfgsb200_objective_t) -> c_int;
+    pub fn lbfgsb200_objective_set_lj_fast(objective: *mut lbfgsb200_objective_t, fast: c_int) -> c_int;
 
     pub fn lbfgsb200_linesearch_begin(param: *const lbfgsb200_param_t, orthantwise: c_int, finit: f64, dginit: f64, step: f64)
         -> *mut lbfgsb200_linesearch_t;

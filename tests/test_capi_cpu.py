@@ -106,3 +106,18 @@ def test_product_never_references_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "lbfgs_oracle" not in txt, f
+
+
+def test_rust_sys_crate_binds_every_declared_symbol():
+    """The Rust `-sys` crate cannot be compiled here (no rustc), but it must at least declare exactly the functions
+    include/lbfgsb200.h declares — no missing and no stale binding."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "lbfgsb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lbfgsb200_[a-z0-9_]+)\s*\(", header))
+    declared -= {n for n in declared if n.endswith("_fn") or n.endswith("_t")}
+    rs = open(os.path.join(root, "rust_lbfgs_b200", "rust", "lbfgs-b200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (lbfgsb200_[a-z0-9_]+)\s*\(", rs))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    assert "LBFGSB200_ABI_VERSION: c_int = 3" in rs

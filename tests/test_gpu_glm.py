@@ -1,7 +1,8 @@
 """The fused one-pass GLM objective (csrc/objectives.cu: k_glm_fused, rows staged by TMA bulk copies) against
 the oracle's objective (tests/owlqn.rs:22-43 for Poisson; the logistic definition in oracle/lbfgs_oracle.cpp)
 and against the two-pass kernels, over the shapes that select every template instantiation and the fallbacks:
-odd ncol (unaligned rows -> two-pass), nrow < number of CTAs, ragged last column pair slots, ncol up to 10240."""
+odd ncol (8-byte aligned rows: scalar shared-memory reads, even rows per stage), nrow < number of CTAs, ragged last
+column pair slots, ncol up to 10 240 per CTA and beyond it with the columns split over a thread-block cluster."""
 import ctypes as C
 import os
 import subprocess
@@ -15,8 +16,15 @@ from gpu_util import ck, dev, host, stream
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(7, 2), (500, 22), (1000, 512), (333, 1000), (4097, 2050), (64, 4096), (200, 6144), (300, 8190),
-          (150, 10000), (150, 10240), (500, 21), (100, 10242)]
+P2, FUSED, ODD, CLUSTER = R._lib.GLM_PATH_TWO_PASS, R._lib.GLM_PATH_FUSED, R._lib.GLM_PATH_FUSED_ODD, R._lib.GLM_PATH_FUSED_CLUSTER
+# (nrow, ncol, the kernels that must have run)
+SHAPES = [(7, 2, FUSED), (500, 22, FUSED), (1000, 512, FUSED), (333, 1000, FUSED), (4097, 2050, FUSED), (64, 4096, FUSED),
+          (200, 6144, FUSED), (300, 8190, FUSED), (150, 10000, FUSED), (150, 10240, FUSED),
+          # odd ncol (rows 8-byte aligned): the reference's own fixture shape, short last groups with an odd row count
+          (500, 21, ODD), (501, 21, ODD), (7, 1, ODD), (333, 1001, ODD), (129, 4097, ODD), (75, 6143, ODD), (40, 6145, P2),
+          # ncol > 10 240: columns split over a thread-block cluster of 2 / 4 / 8 CTAs
+          (100, 10242, CLUSTER), (150, 20000, CLUSTER), (77, 20480, CLUSTER), (60, 40000, CLUSTER), (30, 81920, CLUSTER),
+          (20, 20001, P2)]
 
 
 def eval_gpu(obj, w):
@@ -28,9 +36,9 @@ def eval_gpu(obj, w):
     return float(host(fd)[0]), host(gd)
 
 
-@pytest.mark.parametrize("nrow,ncol", SHAPES)
+@pytest.mark.parametrize("nrow,ncol,path", SHAPES)
 @pytest.mark.parametrize("kind", ["poisson", "logistic"])
-def test_glm_objective_matches_oracle(oracle, kind, nrow, ncol):
+def test_glm_objective_matches_oracle(oracle, kind, nrow, ncol, path):
     rng = np.random.default_rng(nrow * 131 + ncol)
     X = rng.standard_normal((nrow, ncol)) / np.sqrt(ncol)
     X[:, 0] = 1.0
@@ -43,6 +51,7 @@ def test_glm_objective_matches_oracle(oracle, kind, nrow, ncol):
     fr = getattr(oracle.lib(), "oracle_eval_" + kind)(ob.user, w.ctypes.data, gr.ctypes.data, ncol, C.byref(err))
     obj = R.Glm(kind, dev(X), dev(y))
     f, g = eval_gpu(obj, w)
+    assert R.lib().lbfgsb200_objective_last_path(obj._user_ptr(0)) == path
     scale = max(abs(fr), float(np.sum(np.abs(y)) + nrow))
     assert abs(f - fr) <= 1e-12 * scale, (f, fr)
     assert np.max(np.abs(g - gr)) <= 1e-11 * max(np.max(np.abs(gr)), 1.0)
