@@ -140,6 +140,10 @@ typedef int (*lbfgsb200_trial_eval_fn)(void *user, const double *xp_dev, const d
  * keeps one; only {f, g.d} of the rejected ones are ever used (src/line.rs:283-320, :741-760).  So a trial is a
  * PROBE that reads xp and d and writes nothing (2R instead of the fused trial's 2R 2W):
  *   out_dev[0..3] = partial f(xp + step*d), g.d, g.g, x.x          (same sums as lbfgsb200_trial_eval_fn)
+ * step_dev non-NULL: the trial step is *step_dev — device memory written by an earlier kernel on the stream — and
+ * `step` is ignored.  Because a probe writes nothing it can be launched SPECULATIVELY: the solver enqueues the next
+ * iteration's first trial right behind the two-loop recursion (its step, min(max_step_size, |d|) / |d|, is formed
+ * on the device), so that trial's result arrives with the update's own scalars in one host synchronisation.
  * and, once the search has accepted a step, ONE COMMIT pass materialises the point and performs
  * IterationData::update's vector work (src/lbfgs.rs:640-656, :670-673) on the way:
  *   x = xp + step*d;  g = grad f(x);  s = x - xp;  y = g - gp
@@ -151,7 +155,7 @@ typedef int (*lbfgsb200_trial_eval_fn)(void *user, const double *xp_dev, const d
  * the unfused kernels (no FMA), so that all three paths produce the same bits.  Same rules as lbfgsb200_eval_fn:
  * enqueue on `stream`, do not synchronise, non-zero = Err.  Not used for OWL-QN. */
 typedef int (*lbfgsb200_probe_fn)(void *user, const double *xp_dev, const double *d_dev, double step,
-                                  int64_t n_local, void *stream, double *out_dev);
+                                  const double *step_dev, int64_t n_local, void *stream, double *out_dev);
 typedef int (*lbfgsb200_commit_fn)(void *user, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                    double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                    double *y_dev, int64_t n_local, void *stream, double *out_dev);
@@ -414,7 +418,7 @@ int  lbfgsb200_objective_has_trial_eval(const lbfgsb200_objective_t *objective);
  * flags has LBFGSB200_FUSED_SUMS_OVER_RANKS once lbfgsb200_objective_set_shard attached a communicator whose
  * peer mailboxes the kernels can use). */
 int  lbfgsb200_objective_probe(void *objective, const double *xp_dev, const double *d_dev, double step,
-                               int64_t n_local, void *stream, double *out_dev);
+                               const double *step_dev, int64_t n_local, void *stream, double *out_dev);
 int  lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                 double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                 double *y_dev, int64_t n_local, void *stream, double *out_dev);

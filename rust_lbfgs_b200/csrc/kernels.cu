@@ -660,6 +660,15 @@ void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n,
                   (k_dot<false><<<grid, threads_for(L), 0, L.stream>>>({x, y}, n, ws_for(L), out)));
 }
 
+__global__ void k_next_step(const double *dots, double max_step, int constrain, double *step_out) {
+    const double dnorm = sqrt(__ldcg(dots));                                  // lbfgs.rs:543
+    *step_out = constrain ? fmin(max_step, dnorm) / dnorm : 1.0;              // :547-551, the host's own expression
+}
+void launch_next_step(const Launch &L, const double *dots, double max_step, bool constrain, double *step_out) {
+    count(L);
+    k_next_step<<<1, 1, 0, L.stream>>>(dots, max_step, constrain ? 1 : 0, step_out);
+}
+
 __global__ void k_peer_allreduce(PeerCtx pc, double *buf, int count) {
     __shared__ double tab[kMaxPeers + 1][kMailVals];
     if (threadIdx.x < count) tab[kMaxPeers][threadIdx.x] = buf[threadIdx.x];

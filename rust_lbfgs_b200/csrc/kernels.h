@@ -69,12 +69,17 @@ void launch_vecdot(const Launch &L, const double *x, const double *y, int64_t n,
 // stand-alone 1-warp kernel (for results that were not produced by one of the reducing kernels above)
 void launch_peer_allreduce(const Launch &L, double *buf, int count);
 
+// *step_out = constrain ? min(max_step, |d|) / |d| : 1 with |d| = sqrt(dots[0])  (src/lbfgs.rs:543-551), formed on the
+// device so that the next iteration's first (speculative, write-free) trial can be enqueued without a host round trip
+void launch_next_step(const Launch &L, const double *dots, double max_step, bool constrain, double *step_out);
+
 // The launch-bound regime (small.cu): the whole two-loop recursion (2 * bound trips) in ONE thread-block-cluster
 // kernel; q stays in shared memory, the dependent dot products are reduced over DSMEM.  `ring` = S_0 (the ring
 // vectors S_0, Y_0, S_1, ... lie `stride` doubles apart); out = {d.d before projection, g.d | pg.d, d.d after}.
 int64_t two_loop_small_max_n();
 cudaError_t launch_two_loop_small(const Launch &L, int device, int64_t n, int m, int bound, int slot_new, double *d,
                                   const double *dsrc, double *ring, int64_t stride, double *ys_dev, const double *hist,
-                                  double *out, bool owl, int64_t start, int64_t end, int64_t goff);
+                                  double *out, bool owl, int64_t start, int64_t end, int64_t goff, double max_step,
+                                  bool constrain, double *step_out);
 
 }  // namespace lb

@@ -143,7 +143,8 @@ struct RosenProbeOp {
 };
 template <bool S>
 __global__ void __launch_bounds__(kThreads, kProbePrefetch ? 1 : kMinBlocks)
-k_rosenbrock_probe(RosenProbeOp<S> op, int64_t n, ReduceWs ws, double *out) {
+k_rosenbrock_probe(RosenProbeOp<S> op, const double *step_dev, int64_t n, ReduceWs ws, double *out) {
+    if (step_dev) op.step = __ldcg(step_dev);   // a speculative trial: the step was formed on the device
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (kProbePrefetch) stream_pairs_prefetch<4, kUt>(n, op, acc);
     else stream_pairs<4, kUt>(n, op, acc);
@@ -709,6 +710,33 @@ __global__ void __launch_bounds__(kLjTile) k_lj(const double *__restrict__ x, do
 // for bit.  P is chosen so that the grid has >= 16 CTAs per SM: one thread per atom gives 1e5 atoms only 2.7 CTAs
 // per SM (30 % of the warps a B200 can hold, and a 3-vs-2 CTA imbalance between SMs); with 8 lanes per atom the
 // FP64 pipe — the roofline of this kernel — stays busy.  FAST selects lj_pair_fast.
+// One tile of partners for one lane.  SELF: the tile may contain atom i itself (and partners on both sides of it), so
+// every pair checks j != i and j < i; otherwise those tests are hoisted out of the loop: all partners of a tile
+// BELOW atom i's tile have j < i (energy counted), all of a tile ABOVE have j > i (no energy term is even computed).
+// For 1e5 atoms 99.7 % of the tiles take the test-free paths.
+template <int P, bool FAST, bool SELF, bool BELOW>
+__device__ __forceinline__ void lj_tile(const double *__restrict__ sp, int cnt, int sub, int base, int i, double pi0,
+                                        double pi1, double pi2, double eps, double sigma, double eps4, double eps24,
+                                        double sigma2, double &f0, double &f1, double &f2, double &e) {
+#pragma unroll 4
+    for (int jj = sub; jj < cnt; jj += P) {
+        const bool other = SELF ? (base + jj != i) : true;
+        const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
+        double pe, c0, c1, c2;
+        if (FAST) lj_pair_fast(d0, d1, d2, other, eps4, eps24, sigma2, pe, c0, c1, c2);
+        else lj_pair_ref(d0, d1, d2, other, eps, sigma, pe, c0, c1, c2);
+        if (SELF) {
+            if (base + jj < i) e += pe;
+            if (other) { f0 += c0; f1 += c1; f2 += c2; }
+        } else {
+            if (BELOW) e += pe;
+            f0 += c0;
+            f1 += c1;
+            f2 += c2;
+        }
+    }
+}
+
 template <int P, bool FAST>
 __global__ void __launch_bounds__(kLjTile) k_lj_lanes(const double *__restrict__ x, double *__restrict__ g, int64_t natoms,
                                                       int64_t a0, int64_t nloc, double eps, double sigma, ReduceWs ws,
@@ -717,29 +745,26 @@ __global__ void __launch_bounds__(kLjTile) k_lj_lanes(const double *__restrict__
     constexpr int kAtoms = kLjTile / P;
     const int sub = threadIdx.x % P;
     const int64_t il = (int64_t)blockIdx.x * kAtoms + threadIdx.x / P;
-    const int64_t i = a0 + il;
+    const int i = (int)(a0 + il);                 // atoms are indexed with 32 bits (3 * natoms * 8 B would be 51 GB at 2^31)
     const bool active = il < nloc;
     double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
-    if (active) { pi0 = x[3 * i]; pi1 = x[3 * i + 1]; pi2 = x[3 * i + 2]; }
+    if (active) { pi0 = x[3 * (int64_t)i]; pi1 = x[3 * (int64_t)i + 1]; pi2 = x[3 * (int64_t)i + 2]; }
     const double eps4 = 4.0 * eps, eps24 = 24.0 * eps, sigma2 = sigma * sigma;
+    // the tiles that hold this CTA's own atoms (CTA-uniform): only they need the per-pair self / order tests
+    const int first_atom = (int)(a0 + (int64_t)blockIdx.x * kAtoms);
+    const int tile_lo = first_atom / kLjTile, tile_hi = (first_atom + kAtoms - 1) / kLjTile;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
-    for (int64_t base = 0; base < natoms; base += kLjTile) {
-        const int64_t cnt = (natoms - base < kLjTile) ? (natoms - base) : kLjTile;
+    const int ntiles = (int)((natoms + kLjTile - 1) / kLjTile);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int base = tile * kLjTile;
+        const int cnt = (natoms - base < kLjTile) ? (int)(natoms - base) : kLjTile;
         __syncthreads();
-        for (int64_t q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * base + q];
+        for (int q = threadIdx.x; q < cnt * 3; q += kLjTile) sp[q] = x[3 * (int64_t)base + q];
         __syncthreads();
         if (!active) continue;
-#pragma unroll 4
-        for (int jj = sub; jj < (int)cnt; jj += P) {
-            const int64_t j = base + jj;
-            const bool other = (j != i);
-            const double d0 = pi0 - sp[3 * jj], d1 = pi1 - sp[3 * jj + 1], d2 = pi2 - sp[3 * jj + 2];
-            double pe, c0, c1, c2;
-            if (FAST) lj_pair_fast(d0, d1, d2, other, eps4, eps24, sigma2, pe, c0, c1, c2);
-            else lj_pair_ref(d0, d1, d2, other, eps, sigma, pe, c0, c1, c2);
-            if (j < i) e += pe;
-            if (other) { f0 += c0; f1 += c1; f2 += c2; }
-        }
+        if (tile < tile_lo) lj_tile<P, FAST, false, true>(sp, cnt, sub, base, i, pi0, pi1, pi2, eps, sigma, eps4, eps24, sigma2, f0, f1, f2, e);
+        else if (tile > tile_hi) lj_tile<P, FAST, false, false>(sp, cnt, sub, base, i, pi0, pi1, pi2, eps, sigma, eps4, eps24, sigma2, f0, f1, f2, e);
+        else lj_tile<P, FAST, true, false>(sp, cnt, sub, base, i, pi0, pi1, pi2, eps, sigma, eps4, eps24, sigma2, f0, f1, f2, e);
     }
 #pragma unroll
     for (int off = P / 2; off > 0; off >>= 1) {
@@ -858,14 +883,15 @@ int trial_impl(Objective *o, const double *xp, const double *d, double step, dou
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
-int probe_impl(Objective *o, const double *xp, const double *d, double step, int64_t n, cudaStream_t stream, double *out) {
+int probe_impl(Objective *o, const double *xp, const double *d, double step, const double *step_dev, int64_t n,
+               cudaStream_t stream, double *out) {
     if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
     if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     const int grid = stream_grid(o, n, kUt);
     const int threads = o->sequential ? 1 : kThreads;
-    if (rosen_streaming(o, n)) k_rosenbrock_probe<true><<<grid, threads, 0, stream>>>({xp, d, step}, n, fused_ws(o), out);
-    else k_rosenbrock_probe<false><<<grid, threads, 0, stream>>>({xp, d, step}, n, fused_ws(o), out);
+    if (rosen_streaming(o, n)) k_rosenbrock_probe<true><<<grid, threads, 0, stream>>>({xp, d, step}, step_dev, n, fused_ws(o), out);
+    else k_rosenbrock_probe<false><<<grid, threads, 0, stream>>>({xp, d, step}, step_dev, n, fused_ws(o), out);
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
@@ -1066,10 +1092,11 @@ int lbfgsb200_objective_trial_eval(void *objective, const double *xp_dev, const 
     return lb::trial_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, x_dev, g_dev, n_local,
                           (cudaStream_t)stream, out_dev);
 }
-int lbfgsb200_objective_probe(void *objective, const double *xp_dev, const double *d_dev, double step, int64_t n_local,
-                              void *stream, double *out_dev) {
+int lbfgsb200_objective_probe(void *objective, const double *xp_dev, const double *d_dev, double step, const double *step_dev,
+                              int64_t n_local, void *stream, double *out_dev) {
     if (!objective || !xp_dev || !d_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
-    return lb::probe_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, n_local, (cudaStream_t)stream, out_dev);
+    return lb::probe_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, step_dev, n_local,
+                          (cudaStream_t)stream, out_dev);
 }
 int lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev, double step,
                                double bs_scale, double *x_dev, double *g_dev, double *s_dev, double *y_dev, int64_t n_local,

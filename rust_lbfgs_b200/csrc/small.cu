@@ -76,6 +76,9 @@ struct SmallArgs {
     double *out;             // {d.d before projection, g.d | pg.d, d.d after projection}
     int owl;
     int64_t start, end, goff;
+    double max_step;         // the next search's first step, formed here: constrain ? min(max_step, |d|) / |d| : 1
+    int constrain;
+    double *step_out;
 };
 
 __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a) {
@@ -175,6 +178,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a
             a.out[0] = acc[0];
             a.out[1] = acc[1];
             a.out[2] = acc[2];
+            const double dnorm = sqrt(acc[0]);                                // lbfgs.rs:543
+            *a.step_out = a.constrain ? fmin(a.max_step, dnorm) / dnorm : 1.0;   // :547-551
         }
         j = jn;
     }
@@ -191,7 +196,8 @@ int64_t two_loop_small_max_n() { return (int64_t)1 << 18; }
 // Returns cudaSuccess, or the launch error (the caller falls back to the multi-kernel chain).
 cudaError_t launch_two_loop_small(const Launch &L, int device, int64_t n, int m, int bound, int slot_new, double *d,
                                   const double *dsrc, double *ring, int64_t stride, double *ys_dev, const double *hist,
-                                  double *out, bool owl, int64_t start, int64_t end, int64_t goff) {
+                                  double *out, bool owl, int64_t start, int64_t end, int64_t goff, double max_step,
+                                  bool constrain, double *step_out) {
     if (m > kSmallMaxM || bound < 1 || n > two_loop_small_max_n()) return cudaErrorInvalidValue;
     // cluster size: ~2048 elements per CTA at least (4 per thread), as few CTAs as that allows, a power of two
     int c = 1;
@@ -207,7 +213,8 @@ cudaError_t launch_two_loop_small(const Launch &L, int device, int64_t n, int m,
     }
     int64_t per = (n + c - 1) / c;
     per = (per + 1) & ~(int64_t)1;
-    SmallArgs a{n, m, bound, slot_new, d, dsrc, ring, stride, ys_dev, hist, out, owl ? 1 : 0, start, end, goff};
+    SmallArgs a{n, m, bound, slot_new, d, dsrc, ring, stride, ys_dev, hist, out, owl ? 1 : 0, start, end, goff,
+                max_step, constrain ? 1 : 0, step_out};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)c);
     cfg.blockDim = dim3(kSmallThreads);
