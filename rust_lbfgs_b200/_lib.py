@@ -71,7 +71,7 @@ EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.
 TRIAL_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
                             C.c_void_p, C.c_void_p)
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Progress))
-PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p)
+PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 COMMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
@@ -142,7 +142,7 @@ def lib():
     _sig(L, "lbfgsb200_damp_y", i32, [vp, vp, i64, dbl, dbl, dbl, vp, pp(i32)])
     _sig(L, "lbfgsb200_two_loop_backward_step", i32, [vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, pp(dbl)])
     _sig(L, "lbfgsb200_two_loop_forward_step", i32, [vp, vp, vp, vp, i64, dbl, dbl, dbl, i32, i64, i64, vp, pp(dbl)])
-    _sig(L, "lbfgsb200_objective_probe", i32, [vp, vp, vp, dbl, i64, vp, vp])
+    _sig(L, "lbfgsb200_objective_probe", i32, [vp, vp, vp, dbl, vp, i64, vp, vp])
     _sig(L, "lbfgsb200_objective_commit", i32, [vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, i64, vp, vp])
     _sig(L, "lbfgsb200_objective_fused_ops", i32, [vp, pp(FusedOps)])
     _sig(L, "lbfgsb200_profile_enable", i32, [vp, i32])

@@ -102,7 +102,7 @@ int scratch_acquire(const DeviceInfo &dev, size_t scal_count, Scratch *out) {
     s.device = dev.device;
     s.scal_count = scal_count < 256 ? 256 : scal_count;   // room for alpha[m] up to m ~ 200 without a re-allocation
     if (cudaMalloc((void **)&s.scal_dev, sizeof(double) * s.scal_count) != cudaSuccess ||
-        cudaMallocHost((void **)&s.scal_host, sizeof(double) * kMaxAcc * 2) != cudaSuccess ||
+        cudaMallocHost((void **)&s.scal_host, sizeof(double) * 64) != cudaSuccess ||   // Solver::kHostWords
         alloc_reduce_ws(dev, &s.ws) != 0) {
         scratch_free(s);
         return LBFGSB200_ERR_CUDA;
@@ -312,6 +312,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     memset(&prof_, 0, sizeof(prof_));
     graphs_enabled_ = env_int("LBFGSB200_GRAPHS", 1) != 0;
     small_enabled_ = env_int("LBFGSB200_SMALL", 1) != 0;
+    speculate_ = env_int("LBFGSB200_SPECULATE", 1) != 0;
     ring_stride_ = vec_bytes / (int64_t)sizeof(double);
     return 0;
 }
@@ -420,6 +421,19 @@ int Solver::fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2) {
     return rc != 0 ? rc : check_peers(h2, c2);
 }
 
+// Every slot (already summed over the ranks) with one copy and one synchronisation: hall[slot * kMaxAcc + i].
+int Solver::fetch_all(double *hall) {
+    constexpr int kAll = SLOT_COUNT * kMaxAcc;
+    cudaError_t e = cudaMemcpyAsync(scal_host_, scal_dev_, sizeof(double) * kAll, cudaMemcpyDeviceToHost, stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H scalars)");
+    e = cudaStreamSynchronize(stream_);
+    prof_.host_syncs += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if (timing_) prof_resolve();
+    for (int i = 0; i < kAll; ++i) hall[i] = scal_host_[i];
+    return check_peers(hall + SLOT_HIST * kMaxAcc, 5);
+}
+
 // Problem::evaluate (src/core.rs:119-132) followed by the reductions the driver needs at this
 // point: g.d for the line search, g.g (pg.pg) and x.x for Progress / the stop test.
 bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
@@ -459,8 +473,8 @@ bool Solver::evaluate_point(const double *d_or_null, double *dg_out) {
 // An Err from evaluate on any rank must be seen by every rank (replicated control flow): the flag is summed
 // over the ranks with the dot products.
 void Solver::post_eval_flag(int erc) {
-    scal_host_[kMaxAcc] = erc != 0 ? 1.0 : 0.0;   // every trial ends with a stream sync, so the word is free again
-    const cudaError_t e = cudaMemcpyAsync(slot(SLOT_EVAL) + 7, scal_host_ + kMaxAcc, sizeof(double),
+    scal_host_[kFlagWord] = erc != 0 ? 1.0 : 0.0;   // every trial ends with a stream sync, so the word is free again
+    const cudaError_t e = cudaMemcpyAsync(slot(SLOT_EVAL) + 7, scal_host_ + kFlagWord, sizeof(double),
                                           cudaMemcpyHostToDevice, stream_);
     if (e != cudaSuccess) cuda_fail(e, "cudaMemcpyAsync(H2D evaluate flag)");
 }
@@ -500,7 +514,7 @@ bool Solver::trial_point(const double *xp, double stp, double *dg_out) {
         const bool probe = use_probe();
         const int kind = probe ? LBFGSB200_K_PROBE : LBFGSB200_K_TRIAL_EVAL;
         prof_begin(kind);
-        const int erc = probe ? fused_.probe(fused_.user, xp, d_, stp, n_, (void *)stream_, slot(SLOT_EVAL))
+        const int erc = probe ? fused_.probe(fused_.user, xp, d_, stp, nullptr, n_, (void *)stream_, slot(SLOT_EVAL))
                               : fused_.trial(fused_.user, xp, d_, stp, x, gbuf_[cur_g_], n_, (void *)stream_, slot(SLOT_EVAL));
         prof_end(kind, (probe ? 2.0 : 4.0) * vbytes);
         launch_counter_ += 1;
@@ -553,6 +567,7 @@ int Solver::build(double *x_dev, lbfgsb200_eval_fn eval, void *user) {
     last_status_ = 0;
     err_.clear();
     built_ = false;
+    spec_.valid = false;
 
     if (!evaluate_point(nullptr, nullptr)) {  // :454
         if (last_status_ != 0) return last_status_;
@@ -679,7 +694,8 @@ int Solver::two_loop_small(const Launch &L, int64_t bound, int *so_last) {
     prof_begin(LBFGSB200_K_UPDATE_SMALL);
     const cudaError_t e = launch_two_loop_small(L, dev_.device, n_, (int)m_, (int)bound, (int)end_, d_, owl_ ? pg_ : gbuf_[cur_g_],
                                                 S_[0], ring_stride_, ys_dev_, slot(SLOT_HIST), slot(SLOT_LOOP_A), owl_,
-                                                owl_start_, owl_end_, goff_);
+                                                owl_start_, owl_end_, goff_, p_.max_step_size, p_.constrain_step_size != 0,
+                                                slot(SLOT_STEP));
     if (e != cudaSuccess) {   // refused (cluster shape / shared memory): never try again, use the chain
         cudaGetLastError();
         if (timing_ && ((timing_mask_ >> LBFGSB200_K_UPDATE_SMALL) & 1u)) {   // undo prof_begin's pending record
@@ -804,10 +820,24 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     }
     double stp = 0.0, stp_eval = 0.0;   // stp_eval: the step of the last EVALUATED trial, i.e. where x is (line.rs:396-398
                                         // leaves `stp` one update ahead when the search runs out of trials)
+    Speculation spec = spec_;
+    spec_.valid = false;
     while (ls.next_trial(&stp)) {
         double dg = 0.0;
         stp_eval = stp;
-        const bool ok = trial_point(xp, stp, &dg);
+        bool ok;
+        if (spec.valid && spec.step == stp && use_probe()) {
+            // this trial was probed behind the previous update and came back with its scalars: no launch, no round trip
+            neval_ += 1;
+            fx_ = spec.h[0];
+            dg = spec.h[1];
+            gg_ = spec.h[2];
+            xx_ = spec.h[3];
+            ok = true;
+        } else {
+            ok = trial_point(xp, stp, &dg);
+        }
+        spec.valid = false;
         if (!ok && last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;  // CUDA / NCCL failure is fatal
         ls.feed(ok, fx_, dg);
     }
@@ -834,15 +864,43 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     int rc = 0;
     rc = enqueue_history(L, xp, gp, stp_eval);
     if (rc != 0) return rc;
-    if (small_eligible()) rc = two_loop_small(L, bound, &so_last);
+    bool small_ran = false;
+    if (small_eligible()) { rc = two_loop_small(L, bound, &so_last); small_ran = small_enabled_; }
     else if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
     else rc = enqueue_two_loop(L, gp, bound, &so_last);
     if (rc != 0) return rc;
     end_ = (end_ + 1) % m_;
+    // The next search's first trial, speculatively: a probe writes nothing, so it can run right behind the two-loop
+    // recursion with its step formed on the device (min(max_step_size, |d|) / |d|, src/lbfgs.rs:547-551) and return
+    // with the update's own scalars — an iteration whose search accepts its first trial then costs ONE host
+    // round trip instead of two.  Unused (the solve stops, the search wants another first step) it is just dropped.
+    const bool multi = comm_ && comm_size(comm_) > 1;
+    bool speculated = false;
+    if (speculate_ && use_probe() && (!multi || fused_exchanges())) {
+        if (!small_ran)   // (the cluster kernel forms the step in its own epilogue)
+            launch_next_step(L, slot(so_last), p_.max_step_size, p_.constrain_step_size != 0, slot(SLOT_STEP));
+        prof_begin(LBFGSB200_K_PROBE);
+        const int erc = fused_.probe(fused_.user, xbuf_[cur_x_], d_, 0.0, slot(SLOT_STEP), n_, (void *)stream_, slot(SLOT_EVAL));
+        prof_end(LBFGSB200_K_PROBE, 2.0 * vbytes);
+        launch_counter_ += 1;
+        speculated = erc == 0;
+    }
     // the one host round trip of the update: the history sums and the final dot products together
     double h[5], hd[3];
-    rc = fetch2(SLOT_HIST, 5, h, so_last, 3, hd);
-    if (rc != 0) return rc;
+    Speculation next_spec;
+    if (speculated) {
+        double hall[SLOT_COUNT * kMaxAcc];
+        rc = fetch_all(hall);
+        if (rc != 0) return rc;
+        for (int i = 0; i < 5; ++i) h[i] = hall[SLOT_HIST * kMaxAcc + i];
+        for (int i = 0; i < 3; ++i) hd[i] = hall[so_last * kMaxAcc + i];
+        next_spec.valid = true;
+        next_spec.step = hall[SLOT_STEP * kMaxAcc];
+        for (int i = 0; i < 4; ++i) next_spec.h[i] = hall[SLOT_EVAL * kMaxAcc + i];
+    } else {
+        rc = fetch2(SLOT_HIST, 5, h, so_last, 3, hd);
+        if (rc != 0) return rc;
+    }
     const double ss = h[0], ys = h[1], yy = h[2], sbs = h[4];
     if (!(std::sqrt(ss) != 0.0)) {  // :645-646
         char msg[96];
@@ -859,6 +917,7 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     if (owl_ && !(std::sqrt(hd[2]) != 0.0))                                                  // orthantwise.rs:160
         return fail(LBFGSB200_ERR_OWLQN_ZERO_DIRECTION, "invalid direction vector after constraints");
 
+    spec_ = next_spec;            // the update was sound: the speculative trial (if any) belongs to the next search
     fill_progress(out, step_ls);  // :556-557
     return 0;
 }

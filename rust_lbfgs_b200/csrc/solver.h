@@ -74,8 +74,9 @@ class Solver {
         fused_ = lbfgsb200_fused_ops_t{};
         fused_.trial = fn;
         fused_.user = user;
+        spec_.valid = false;
     }
-    void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; }
+    void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; spec_.valid = false; }
 
     // timing: 0 = off, 1 = every kernel kind, otherwise a mask: bit (1 + kind) times LBFGSB200_K_<kind> only
     void profile_enable(int timing) { timing_ = timing != 0; timing_mask_ = (timing == 1) ? ~0u : ((unsigned)timing >> 1); }
@@ -84,7 +85,10 @@ class Solver {
 
   private:
     // scalar slots in device memory (kMaxAcc doubles each)
-    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_COUNT = 5 };
+    // SLOT_STEP[0]: the next search's first step as formed on the device (speculative first trial)
+    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_STEP = 5, SLOT_COUNT = 6 };
+    static constexpr int kHostWords = 64;       // pinned mirror: every slot (48 doubles) + the evaluate-flag staging word
+    static constexpr int kFlagWord = 56;
     double *slot(int s) const { return scal_dev_ + (size_t)s * kMaxAcc; }
 
     int fail(int status, const char *msg);
@@ -99,6 +103,7 @@ class Solver {
     void post_eval_flag(int erc);
     int fetch(int s, int count, double *host, bool ours = true);   // allreduce + D2H + sync of a slot
     int fetch2(int s1, int c1, double *h1, int s2, int c2, double *h2);  // two reduced slots, one sync
+    int fetch_all(double *hall);                                   // every slot with one copy and one sync
     int check_peers(const double *h, int count);                   // NaN sums + the communicator's fault word => ERR_NCCL
     // ours = the slot was produced by one of our reducing kernels (already exchanged inside it with peer mailboxes)
     int reduce_across_ranks(int s, int count, bool ours = true);
@@ -152,6 +157,11 @@ class Solver {
     lbfgsb200_eval_fn eval_ = nullptr;
     void *eval_user_ = nullptr;
     lbfgsb200_fused_ops_t fused_{};
+    // The next iteration's first trial, probed speculatively behind the two-loop recursion (write-free, so harmless
+    // if it is never used): its step and {f, g.d, g.g, x.x}.  Consumed by the next propagate() if the line search
+    // asks for exactly that step.
+    struct Speculation { bool valid = false; double step = 0.0; double h[4] = {0.0, 0.0, 0.0, 0.0}; } spec_;
+    bool speculate_ = true;       // LBFGSB200_SPECULATE=0 disables
     bool built_ = false;
     double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point
     double dginit_ = 0.0;                      // g.d (pg.d) for the next line search

@@ -107,7 +107,7 @@ pub type lbfgsb200_eval_fn = Option<unsafe extern "C" fn(user: *mut c_void, x_de
 pub type lbfgsb200_trial_eval_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
     step: f64, x_dev: *mut f64, g_dev: *mut f64, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
 pub type lbfgsb200_probe_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64,
-    n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
+    step_dev: *const f64, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
 pub type lbfgsb200_commit_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
     gp_dev: *const f64, step: f64, bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
     n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
@@ -221,8 +221,8 @@ extern "C" {
     pub fn lbfgsb200_objective_trial_eval(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64, x_dev: *mut f64,
                                           g_dev: *mut f64, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
     pub fn lbfgsb200_objective_has_trial_eval(objective: *const lbfgsb200_objective_t) -> c_int;
-    pub fn lbfgsb200_objective_probe(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64, n_local: i64,
-                                     stream: *mut c_void, out_dev: *mut f64) -> c_int;
+    pub fn lbfgsb200_objective_probe(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, step: f64, step_dev: *const f64,
+                                     n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
     pub fn lbfgsb200_objective_commit(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
                                       bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
                                       n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;

@@ -273,7 +273,7 @@ def test_fused_trial_kernel_direct(oracle):
             assert abs(got - want) <= 1e-13 * max(abs(want), float(np.abs(gr).max() * np.abs(d).max())), (n, got, want)
         # the write-free probe: the same four sums, bit for bit, and no stores
         out2 = torch.zeros(8, dtype=torch.float64, device="cuda:0")
-        ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), step, n, stream(), out2.data_ptr()))
+        ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xpd.data_ptr(), dd.data_ptr(), step, None, n, stream(), out2.data_ptr()))
         torch.cuda.synchronize()
         assert np.array_equal(host(out2)[:4], o[:4]), n
         # the commit: x, g as the trial wrote them; s = x - xp, y = g - gp bit-exact; the sums of lbfgsb200_history_update
@@ -303,3 +303,37 @@ def test_fused_trial_kernel_direct(oracle):
     assert ops.trial and ops.probe and ops.commit and ops.flags == R._lib.FUSED_COMMIT_SKIPS_GP
     assert L.lbfgsb200_objective_has_trial_eval(lj._user_ptr(0)) == 0
     assert L.lbfgsb200_objective_has_trial_eval(obj._user_ptr(0)) == 1
+
+
+def test_speculative_first_trial_is_transparent(monkeypatch):
+    """The next search's first trial is probed speculatively behind the two-loop recursion (its step formed on the
+    device) and returns with the update's scalars.  With and without it the solve is the same bit for bit — every line
+    search, damping, searches that clip or re-do their first step — and it saves one host round trip per iteration."""
+    import torch
+
+    def run(spec, builder, x0):
+        monkeypatch.setenv("LBFGSB200_SPECULATE", "1" if spec else "0")
+        return gpu_minimize(builder(), x0, R.Rosenbrock())
+    for name, builder in (
+            ("MoreThuente", lambda: R.lbfgs().with_max_iterations(40)),
+            ("Armijo + damping", lambda: R.lbfgs().with_linesearch_algorithm("BacktrackingArmijo").with_damping(True).with_max_iterations(40)),
+            ("StrongWolfe", lambda: R.lbfgs().with_linesearch_algorithm("BacktrackingStrongWolfe").with_max_iterations(40)),
+            ("min_step clips the first trial", lambda: R.lbfgs().with_linesearch_min_step(0.05).with_max_iterations(25)),
+            ("no step-size cap", lambda: R.lbfgs().with_max_step_size(1e20).with_max_iterations(40)),
+            ("sequential sums", lambda: seq().with_max_iterations(30))):
+        for n in (100, 5000, 300_000):
+            x0 = perturbed_x0(n, seed=5)
+            _same_traces(run(True, builder, x0), run(False, builder, x0), f"{name} n={n}")
+    # and it does save the round trip: host synchronisations per iteration = evaluations, not evaluations + 1
+    syncs = {}
+    for spec in (True, False):
+        monkeypatch.setenv("LBFGSB200_SPECULATE", "1" if spec else "0")
+        x = torch.tensor(perturbed_x0(4096), device="cuda:0")
+        st = R.lbfgs().build(x, R.Rosenbrock())
+        st.profile_reset()
+        evals = 0
+        for _ in range(21):
+            evals += st.propagate().ncall
+        syncs[spec] = (st.profile()["host_syncs"], evals)
+        st.close()
+    assert syncs[False][0] == syncs[False][1] + 20 and syncs[True][0] <= syncs[True][1] + 1, syncs

@@ -224,7 +224,7 @@ def test_probe_and_commit_random(oracle, n):
     gp, f0 = torch.empty_like(xp), torch.zeros(1, dtype=torch.float64, device="cuda:0")
     ck(L.lbfgsb200_objective_eval(obj._user_ptr(0), xp.data_ptr(), gp.data_ptr(), n, stream(), f0.data_ptr()))
     out = torch.zeros(8, dtype=torch.float64, device="cuda:0")
-    ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xp.data_ptr(), d.data_ptr(), step, n, stream(), out.data_ptr()))
+    ck(L.lbfgsb200_objective_probe(obj._user_ptr(0), xp.data_ptr(), d.data_ptr(), step, None, n, stream(), out.data_ptr()))
     x, g, s, y = (torch.empty_like(xp) for _ in range(4))
     outc = torch.zeros(8, dtype=torch.float64, device="cuda:0")
     ck(L.lbfgsb200_objective_commit(obj._user_ptr(0), xp.data_ptr(), d.data_ptr(), gp.data_ptr(), step, bs_scale,
