@@ -117,20 +117,23 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a
             if (first && rank == 0) a.ys_dev[j] = ys_j;     // keep y.s of the newest pair for the next m iterations (:653)
         }
         const double nalpha = -alpha;
-        const double *y = a.ring + (int64_t)(2 * j + 1) * a.stride + lo;
-        const double *sn = a.ring + (int64_t)(2 * jn) * a.stride + lo;
-        const double *src = a.dsrc + lo;
+        // read-only for the whole kernel (the ring and g were written by earlier launches): ld.global.nc, so the
+        // loads of an unrolled body are issued together instead of waiting behind the shared-memory stores of q
+        const double *__restrict__ y = a.ring + (int64_t)(2 * j + 1) * a.stride + lo;
+        const double *__restrict__ sn = a.ring + (int64_t)(2 * jn) * a.stride + lo;
+        const double *__restrict__ src = a.dsrc + lo;
         double acc[1] = {0.0};
-#pragma unroll 4
+#pragma unroll 8
         for (int64_t i = tid; i < cnt; i += kSmallThreads) {
-            double qi = first ? -src[i] : q[i];             // vecncpy, core.rs:99
-            const double yi = y[i];
+            const double qi = first ? -__ldg(src + i) : q[i];   // vecncpy, core.rs:99
+            const double yi = __ldg(y + i);
+            const double si = last ? 0.0 : __ldg(sn + i);
             double v = qi + nalpha * yi;                    // vecadd(y, -alpha), :589
             if (last) {
                 v = v * gamma;                              // vecscale(gamma), :591
                 acc[0] += yi * v;                           // y_j . d for the first beta, :597
             } else {
-                acc[0] += sn[i] * v;                        // s_{j-1} . q for the next alpha, :587
+                acc[0] += si * v;                           // s_{j-1} . q for the next alpha, :587
             }
             q[i] = v;
         }
@@ -144,23 +147,24 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a
         const int jn = (j + 1) % m;
         const double beta = red / ys_s[j];                  // :597
         const double coef = alpha_s[j] - beta;              // :599
-        const double *s = a.ring + (int64_t)(2 * j) * a.stride + lo;
-        const double *aux = last ? a.dsrc + lo : a.ring + (int64_t)(2 * jn + 1) * a.stride + lo;
+        const double *__restrict__ s = a.ring + (int64_t)(2 * j) * a.stride + lo;
+        const double *__restrict__ aux = last ? a.dsrc + lo : a.ring + (int64_t)(2 * jn + 1) * a.stride + lo;
         double acc[3] = {0.0, 0.0, 0.0};
         if (!last) {
-#pragma unroll 4
+#pragma unroll 8
             for (int64_t i = tid; i < cnt; i += kSmallThreads) {
-                const double v = q[i] + coef * s[i];        // vecadd(s, alpha - beta), :599
-                acc[0] += aux[i] * v;                       // y_{j+1} . r for the next beta, :597
+                const double si = __ldg(s + i), ai = __ldg(aux + i);
+                const double v = q[i] + coef * si;          // vecadd(s, alpha - beta), :599
+                acc[0] += ai * v;                           // y_{j+1} . r for the next beta, :597
                 q[i] = v;
             }
             cluster_sum<1>(reinterpret_cast<double(&)[1]>(acc), warp_part, cta_part, parity, cluster, nctas);
         } else {
-            double *dout = a.d + lo;
-#pragma unroll 4
+            double *__restrict__ dout = a.d + lo;
+#pragma unroll 8
             for (int64_t i = tid; i < cnt; i += kSmallThreads) {
-                double v = q[i] + coef * s[i];
-                const double ai = aux[i];
+                const double si = __ldg(s + i), ai = __ldg(aux + i);
+                double v = q[i] + coef * si;
                 acc[0] += v * v;                            // dnorm^2 before projection, :543
                 if (a.owl) {
                     const int64_t gidx = a.goff + lo + i;
