@@ -28,6 +28,7 @@ constexpr int kSmallThreads = 512;
 constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr int kSmallMaxM = 64;
 constexpr int kSmallMaxCluster = 16;
+constexpr int kChunk = 8;   // elements per thread whose loads are issued together
 
 __device__ __forceinline__ double sgn_small(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 
@@ -81,23 +82,6 @@ struct SmallArgs {
     double *step_out;
 };
 
-// Registers holding one trip's first kChunk elements per thread of its two streamed vectors.  They are loaded for
-// trip k + 1 BEFORE trip k's cluster reduction, so the L2 latency of the next trip's operands hides behind the
-// barrier of this one: a trip then costs about one barrier, not barrier + load latency.
-constexpr int kChunk = 16;
-struct Prefetch {
-    double a[kChunk], b[kChunk];
-};
-__device__ __forceinline__ void prefetch(Prefetch &p, const double *__restrict__ va, const double *__restrict__ vb,
-                                         int64_t cnt, int tid) {
-#pragma unroll
-    for (int k = 0; k < kChunk; ++k) {
-        const int64_t i = tid + (int64_t)k * kSmallThreads;
-        p.a[k] = (i < cnt) ? __ldg(va + i) : 0.0;             // read-only for the whole kernel: ld.global.nc
-        p.b[k] = (vb != nullptr && i < cnt) ? __ldg(vb + i) : 0.0;
-    }
-}
-
 __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a) {
     extern __shared__ __align__(16) double q[];             // this CTA's slice of q
     __shared__ double warp_part[3][kSmallWarps];
@@ -112,109 +96,118 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_two_loop_small(SmallArgs a
     per = (per + 1) & ~(int64_t)1;
     const int64_t lo = (int64_t)rank * per;
     const int64_t cnt = (lo >= a.n) ? 0 : ((a.n - lo < per) ? (a.n - lo) : per);
-    const int m = a.m, bound = a.bound, trips = 2 * a.bound;
+    const int m = a.m;
     if (tid < m) ys_s[tid] = a.ys_dev[tid];
     __syncthreads();
     const double ys_new = a.hist[1];
     const double gamma = ys_new / a.hist[2];                // ys / yy of the newest pair (src/lbfgs.rs:691)
     int parity = 0;
     double red = a.hist[3];                                 // s_new . (-g): the first alpha's numerator
-    const double *__restrict__ src = a.dsrc + lo;           // g | pg: the recursion starts from -src, the last trip dots with it
 
-    // The operands of trip k (src/lbfgs.rs:582-601): backward trips walk j = slot_new, slot_new - 1, ... and stream
-    // (y_j, s_{j-1}); forward trips walk back up and stream (s_j, y_{j+1}); the last forward trip dots with g | pg.
-    auto slot_of = [&](int k) {   // ring slot of trip k
-        const int back = (k < bound) ? k : (trips - 1 - k);
-        return ((a.slot_new - back) % m + m) % m;
-    };
-    auto operands = [&](int k, const double *&va, const double *&vb) {
-        const int j = slot_of(k);
-        if (k < bound) {
-            va = a.ring + (int64_t)(2 * j + 1) * a.stride + lo;                                  // y_j
-            vb = (k == bound - 1) ? nullptr : a.ring + (int64_t)(2 * ((j + m - 1) % m)) * a.stride + lo;   // s_{j-1}
-        } else {
-            va = a.ring + (int64_t)(2 * j) * a.stride + lo;                                      // s_j
-            vb = (k == trips - 1) ? src : a.ring + (int64_t)(2 * ((j + 1) % m) + 1) * a.stride + lo;        // y_{j+1} | g
+    // ---- backward loop (src/lbfgs.rs:582-591) ----
+    int j = (a.slot_new + 1) % m;
+    for (int t = 0; t < a.bound; ++t) {
+        j = (j + m - 1) % m;
+        const bool first = (t == 0), last = (t == a.bound - 1);
+        const int jn = (j + m - 1) % m;
+        const double ys_j = first ? ys_new : ys_s[j];
+        const double alpha = red / ys_j;                    // :587
+        if (tid == 0) {
+            alpha_s[j] = alpha;
+            if (first) ys_s[j] = ys_j;
+            if (first && rank == 0) a.ys_dev[j] = ys_j;     // keep y.s of the newest pair for the next m iterations (:653)
         }
-    };
-    Prefetch pf;
-    {
-        const double *va, *vb;
-        operands(0, va, vb);
-        prefetch(pf, va, vb, cnt, tid);
-    }
-    for (int k = 0; k < trips; ++k) {
-        const bool backward = k < bound;
-        const bool first = (k == 0), last_b = (k == bound - 1), last_f = (k == trips - 1);
-        const int j = slot_of(k);
-        const double *va, *vb;
-        operands(k, va, vb);
-        double coef;
-        if (backward) {
-            const double ys_j = first ? ys_new : ys_s[j];
-            const double alpha = red / ys_j;                // :587
-            if (tid == 0) {
-                alpha_s[j] = alpha;
-                if (first) ys_s[j] = ys_j;
-                if (first && rank == 0) a.ys_dev[j] = ys_j;  // keep y.s of the newest pair for the next m iterations (:653)
-            }
-            coef = -alpha;
-        } else {
-            const double beta = red / ys_s[j];              // :597
-            coef = alpha_s[j] - beta;                       // :599
-        }
-        double acc[3] = {0.0, 0.0, 0.0};
+        const double nalpha = -alpha;
+        // read-only for the whole kernel (the ring and g were written by earlier launches): ld.global.nc, so the
+        // loads of an unrolled body are issued together instead of waiting behind the shared-memory stores of q
+        const double *__restrict__ y = a.ring + (int64_t)(2 * j + 1) * a.stride + lo;
+        const double *__restrict__ sn = a.ring + (int64_t)(2 * jn) * a.stride + lo;
+        const double *__restrict__ src = a.dsrc + lo;
+        double acc[1] = {0.0};
+        // kChunk elements per thread at a time, ALL their loads issued (predicated) before the first use: a thread's
+        // few elements cost one L2 latency per chunk instead of one per element (a partially unrolled loop runs
+        // its remainder iterations — here usually all of them — one load-use at a time)
         for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)kChunk * kSmallThreads) {
-            if (i0 != tid) prefetch(pf, va + (i0 - tid), vb ? vb + (i0 - tid) : nullptr, cnt - (i0 - tid), tid);   // slices beyond 8 192 elements
+            double yv[kChunk], sv[kChunk], qv[kChunk];
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c) {
+                const int64_t i = i0 + (int64_t)c * kSmallThreads;
+                const bool in = i < cnt;
+                yv[c] = in ? __ldg(y + i) : 0.0;
+                sv[c] = (in && !last) ? __ldg(sn + i) : 0.0;
+                qv[c] = in ? (first ? -__ldg(src + i) : q[i]) : 0.0;   // vecncpy, core.rs:99
+            }
 #pragma unroll
             for (int c = 0; c < kChunk; ++c) {
                 const int64_t i = i0 + (int64_t)c * kSmallThreads;
                 if (i < cnt) {
-                    if (backward) {
-                        const double qi = first ? -__ldg(src + i) : q[i];   // vecncpy, core.rs:99
-                        double v = qi + coef * pf.a[c];         // vecadd(y, -alpha), :589
-                        if (last_b) {
-                            v = v * gamma;                      // vecscale(gamma), :591
-                            acc[0] += pf.a[c] * v;              // y_j . d for the first beta, :597
-                        } else {
-                            acc[0] += pf.b[c] * v;              // s_{j-1} . q for the next alpha, :587
-                        }
+                    double v = qv[c] + nalpha * yv[c];      // vecadd(y, -alpha), :589
+                    if (last) {
+                        v = v * gamma;                      // vecscale(gamma), :591
+                        acc[0] += yv[c] * v;                // y_j . d for the first beta, :597
+                    } else {
+                        acc[0] += sv[c] * v;                // s_{j-1} . q for the next alpha, :587
+                    }
+                    q[i] = v;
+                }
+            }
+        }
+        cluster_sum<1>(acc, warp_part, cta_part, parity, cluster, nctas);
+        parity ^= 1;
+        red = acc[0];
+    }
+    // ---- forward loop (src/lbfgs.rs:594-601) ----
+    for (int t = 0; t < a.bound; ++t) {
+        const bool last = (t == a.bound - 1);
+        const int jn = (j + 1) % m;
+        const double beta = red / ys_s[j];                  // :597
+        const double coef = alpha_s[j] - beta;              // :599
+        const double *__restrict__ s = a.ring + (int64_t)(2 * j) * a.stride + lo;
+        const double *__restrict__ aux = last ? a.dsrc + lo : a.ring + (int64_t)(2 * jn + 1) * a.stride + lo;
+        double acc[3] = {0.0, 0.0, 0.0};
+        double *__restrict__ dout = a.d + lo;
+        for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)kChunk * kSmallThreads) {
+            double sv[kChunk], av[kChunk];
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c) {
+                const int64_t i = i0 + (int64_t)c * kSmallThreads;
+                const bool in = i < cnt;
+                sv[c] = in ? __ldg(s + i) : 0.0;
+                av[c] = in ? __ldg(aux + i) : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c) {
+                const int64_t i = i0 + (int64_t)c * kSmallThreads;
+                if (i < cnt) {
+                    double v = q[i] + coef * sv[c];         // vecadd(s, alpha - beta), :599
+                    if (!last) {
+                        acc[0] += av[c] * v;                // y_{j+1} . r for the next beta, :597
                         q[i] = v;
                     } else {
-                        double v = q[i] + coef * pf.a[c];       // vecadd(s, alpha - beta), :599
-                        if (!last_f) {
-                            acc[0] += pf.b[c] * v;              // y_{j+1} . r for the next beta, :597
-                            q[i] = v;
-                        } else {
-                            acc[0] += v * v;                    // dnorm^2 before projection, :543
-                            if (a.owl) {
-                                const int64_t gidx = a.goff + lo + i;
-                                if (gidx >= a.start && gidx < a.end && sgn_small(v) != sgn_small(-pf.b[c])) v = 0.0;  // orthantwise.rs:140-147
-                                acc[2] += v * v;                // ||d|| after projection, :160
-                            }
-                            acc[1] += pf.b[c] * v;              // next dginit: g.d or pg.d, core.rs:78-92
-                            a.d[lo + i] = v;
+                        acc[0] += v * v;                    // dnorm^2 before projection, :543
+                        if (a.owl) {
+                            const int64_t gidx = a.goff + lo + i;
+                            if (gidx >= a.start && gidx < a.end && sgn_small(v) != sgn_small(-av[c])) v = 0.0;  // orthantwise.rs:140-147
+                            acc[2] += v * v;                // ||d|| after projection, :160
                         }
+                        acc[1] += av[c] * v;                // next dginit: g.d or pg.d, core.rs:78-92
+                        dout[i] = v;
                     }
                 }
             }
         }
-        if (k + 1 < trips) {   // the next trip's operands do not depend on this trip's dot product: fetch them now
-            const double *na, *nb;
-            operands(k + 1, na, nb);
-            prefetch(pf, na, nb, cnt, tid);
-        }
-        if (last_f) cluster_sum<3>(acc, warp_part, cta_part, parity, cluster, nctas);
+        if (last) cluster_sum<3>(acc, warp_part, cta_part, parity, cluster, nctas);
         else cluster_sum<1>(reinterpret_cast<double(&)[1]>(acc), warp_part, cta_part, parity, cluster, nctas);
         parity ^= 1;
         red = acc[0];
-        if (last_f && rank == 0 && tid == 0) {
+        if (last && rank == 0 && tid == 0) {
             a.out[0] = acc[0];
             a.out[1] = acc[1];
             a.out[2] = acc[2];
             const double dnorm = sqrt(acc[0]);                                // lbfgs.rs:543
             *a.step_out = a.constrain ? fmin(a.max_step, dnorm) / dnorm : 1.0;   // :547-551
         }
+        j = jn;
     }
     if (nctas > 1) cluster.sync();   // no CTA may exit while a peer still reads its partials through DSMEM
 }
