@@ -508,7 +508,23 @@ def run_ours(args):
         "note": "one lbfgsb200_minimize_host_ex() call on a pinned HOST buffer: H2D of x0, solver creation, build, "
                 "W+K iterations, D2H of x, teardown",
     }
-    del xh
+    # what the two bulk copies of that call cost on their own, all ranks copying at the same time (the limiter of
+    # e2e on N GPUs of one host: they share the host's memory and PCIe root complexes)
+    xd = torch.empty(n_local, dtype=torch.float64, device=dev)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    xd.copy_(xh, non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    xh.copy_(xd, non_blocking=True)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    h2d_s, d2h_s = D.max_over_ranks(t1 - t0), D.max_over_ranks(t2 - t1)
+    e2e["bulk_copies_alone"] = {"h2d_seconds": h2d_s, "d2h_seconds": d2h_s,
+                                "h2d_GBps_per_gpu": 8.0 * n_local / 1e9 / h2d_s, "d2h_GBps_per_gpu": 8.0 * n_local / 1e9 / d2h_s,
+                                "share_of_e2e_seconds": (h2d_s + d2h_s) / e2e_s}
+    del xh, xd
     obj.close()
 
     # ---- parity of what was just timed (checker only; rank 0) -----------------------------------------------
