@@ -33,6 +33,7 @@ for v in "$@"; do
     vG) build vG 8 1 4 256 3;;
     vH) build vH 8 1 4 256 4;;
     x-*) IFS=- read -r _ u uh ut <<< "$v"; build "$v" "$u" 1 "$uh" 256 "$ut";;   # x-<U>-<UH>-<UT>
+    s-*) IFS=- read -r _ ld st <<< "$v"; EXTRA2="-DLB_LD_POLICY=$ld -DLB_ST_POLICY=$st" build "$v" 8 1 4 256 6;;   # s-<LD>-<ST>: cache policies, shipped tiles
     p-*) IFS=- read -r _ u uh ut <<< "$v"; EXTRA2="-DLB_PROBE_PREFETCH=1" build "$v" "$u" 1 "$uh" 256 "$ut";;   # the same with the prefetching probe
   esac
 done
