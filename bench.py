@@ -242,13 +242,15 @@ def workload_config(n_local, n_global, m):
 
 # ---------------------------------------------------------------------------------------------------
 def timed_iterations(R, D, dev, comm, world, n_local, m, K, W, fused, barrier, sampler=None, dom="backward",
-                     profile_pass=0):
+                     profile_pass=0, direction=None):
     """W warm-up + K timed L-BFGS iterations on a device-resident x0 = (-1.2, 1) repeated; CUDA events on the
     solver's stream (torch's current stream), max over ranks.  Returns a dict of raw measurements."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     n_global, goff = n_local * world, rank * n_local
     b = R.lbfgs().with_m(m).with_fused_trial(fused)
+    if direction is not None:
+        b = b.with_direction(direction)
     if comm is not None:
         b = b.with_shard(comm, n_global, goff)
     x = torch.empty(n_local, dtype=torch.float64, device=dev)
@@ -385,6 +387,36 @@ def nondegenerate_sharded_parity(R, D, dev, comm, world, rank, n=100_002, iters=
             "bar": "identical status and evaluation counts; x and fx within max(1e-10, 100 x the drift between two CPU "
                    "summation orders of the oracle) in every iteration",
             "bar_met": bool(counts_ok and widened_ok)}
+
+
+def compact_block(R, D, dev, comm, world, rank, n_local, m, K, W, fused, barrier, peak, check, n_ref, unit):
+    """The same workload with the opt-in compact search direction (`with_direction("compact")`, csrc/compact.cu): the
+    reference's recursion and element-wise operations, its 2m scalars from inner products of the unmodified ring
+    vectors — two passes over the ring per iteration instead of 2m dependent ones.  NOT the headline `value` (that
+    is the reference's own arithmetic, trip by trip); reported beside it with its own parity check."""
+    r = timed_iterations(R, D, dev, comm, world, n_local, m, K, W, fused, barrier, None, "forward", direction="compact",
+                         profile_pass=max(3, min(10, K)))
+    launches, kbytes, kms, moved, evals = kernel_tables(r["prof"], n_local, K, r["ms_total"], peak)
+    pa = r["prof_all"]
+    names = {"backward": "pass A (k_gram)", "forward": "pass B (k_direction)", "probe": "probe", "commit": "commit"}
+    out = {
+        "what": "opt-in LBFGSB200_DIRECTION_COMPACT: alpha_j / beta_j from S^T Y, Y^T Y kept on the device; pass A (gram) + "
+                "scalar recursions + pass B (direction) instead of 2m trips; same element-wise arithmetic",
+        "ms_per_step": r["ms_total"] / K, "value": K / (r["ms_total"] / 1e3) * (n_local * world) / n_ref, "unit": unit,
+        "algorithmic_bytes_per_iteration_per_gpu": moved / max(1, K),
+        "algorithmic_GBps_per_gpu": moved / 1e9 / (r["ms_total"] / 1e3),
+        "frac_of_peak_per_gpu": moved / 1e9 / (r["ms_total"] / 1e3) / peak,
+        "evaluations_per_iteration": evals / max(1, K),
+        "direction_kernel_GBps": (kbytes["forward"] / 1e9) / (kms["forward"] / 1e3) if kms["forward"] > 0 else None,
+        "profile_pass_kernel_GBps": {names.get(k, k): round(pa["bytes"][k] / 1e9 / (pa["ms"][k] / 1e3), 1) for k in pa["ms"]
+                                     if pa["ms"][k] > 0 and pa["bytes"][k] > 0},
+        "profile_pass_kernel_ms_per_iteration": {names.get(k, k): round(pa["ms"][k] / max(3, min(10, K)), 3) for k in pa["ms"]
+                                                 if pa["ms"][k] > 0},
+        "launches_per_iteration": sum(launches.values()) / max(1, K),
+        "allreduces": r["prof"]["allreduces"],
+        "parity": isometric_parity(r["seen"], n_local * world, m, 1 + W + K) if (check and rank == 0) else None,
+    }
+    return out
 
 
 def kernel_tables(prof, n_local, K, ms_total, peak):
@@ -540,6 +572,15 @@ def run_ours(args):
         if rank == 0:
             parity["nondegenerate_sharded_solve"] = nd
 
+    # ---- the opt-in compact search direction on the headline workload ------------------------------------------------
+    compact = None
+    if not args.no_compact and m <= 32:
+        try:
+            compact = compact_block(R, D, dev, comm, world, rank, n_local, m, K, W, fused, barrier, peak,
+                                    not args.no_cpu_baseline, N_REF, UNIT)
+        except Exception as e:   # never break the headline measurement
+            compact = {"error": repr(e)}
+
     # ---- BASELINE configs[4]: Rosenbrock n = 2^31, m = 20 sharded over 8 GPUs = 2^28 elements per GPU -----------
     # Run at every N (weak scaling at 2^28 per GPU), so the driver's own N = 1, 2, 4, 8 set yields north_star's
     # "sharded n = 2^31, m = 20 scales >= 6x from 1 to 8 GPUs" from its per-N lines.
@@ -565,6 +606,12 @@ def run_ours(args):
                 "k_backward_GBps": (kb5[DOM] / 1e9) / (km5[DOM] / 1e3) if km5[DOM] > 0 else None,
                 "parity": isometric_parity(r5["seen"], n5 * world, m5, 1 + W5 + K5) if (rank == 0 and not args.no_cpu_baseline) else None,
             }
+            if not args.no_compact:
+                try:
+                    config5["compact_direction"] = compact_block(R, D, dev, comm, world, rank, n5, m5, K5, W5, fused, barrier,
+                                                                 peak, not args.no_cpu_baseline, n5, "it/s x n_global/2^28")
+                except Exception as e:
+                    config5["compact_direction"] = {"error": repr(e)}
         else:
             config5 = {"skipped": f"needs {(2 * m5 + 7) * 8 * n5 / 2**30:.0f} GiB of free HBM, {free_b / 2**30:.0f} GiB free"}
 
@@ -588,7 +635,7 @@ def run_ours(args):
             "run": {"ncall_per_iteration": [s[1] for s in seen], "final_fx": final.fx, "final_gnorm": final.gnorm,
                     "host_numa_cpus": len(cpus) if cpus else None},
             "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "parity": parity, "e2e": e2e,
-            "config5": config5, "gpu_launches": gpu_launches, "clocks": clocks,
+            "compact_direction": compact, "config5": config5, "gpu_launches": gpu_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -613,6 +660,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="cpu_baseline: seconds of timed iterations at most")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline and the oracle-side parity checks")
     ap.add_argument("--no-config5", action="store_true", help="skip the 2^28-per-GPU, m=20 block")
+    ap.add_argument("--no-compact", action="store_true", help="skip the opt-in compact-direction blocks")
     ap.add_argument("--unfused-trial", action="store_true",
                     help="line-search trials as K1 + evaluate + K2 (three passes)")
     ap.add_argument("--fused-trial-only", action="store_true",

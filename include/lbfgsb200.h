@@ -245,6 +245,27 @@ int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eva
  * `trial` it runs the one-pass trial; otherwise K1 + evaluate + K2.  All three give the same bits. */
 int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_ops_t *ops);
 
+/* How the search direction H.(-g) of src/lbfgs.rs:569-604 is formed (an extension; the reference has one way).
+ *   TWO_LOOP (default)  the reference's recursion, one fused pass per trip: 2 * min(m, k) dependent passes over the
+ *                       vector, (8 b - 1) V of memory traffic, 2 b reductions (and 2 b cross-GPU exchanges).
+ *   COMPACT             the same recursion with the same element-wise operations in the same order, but its 2 b
+ *                       scalars alpha_j / beta_j come from inner products of the UNMODIFIED ring vectors (S^T Y and
+ *                       Y^T Y are kept on the device across iterations): two passes over the ring, (4 b + 4) V, 2
+ *                       reductions, one all-reduce.  Given equal scalars d is bit-identical; the scalars differ from
+ *                       the reference's by rounding only — less than the reference's own sensitivity to the order
+ *                       in which its dot products are summed.  m <= 32.
+ * Call before build() / minimize().  The environment variable LBFGSB200_DIRECTION=compact makes COMPACT the default
+ * of every solver created afterwards (that is how lbfgsb200_minimize_host* pick it up). */
+enum {
+    LBFGSB200_DIRECTION_TWO_LOOP = 0,
+    LBFGSB200_DIRECTION_COMPACT = 1
+};
+int lbfgsb200_set_direction(lbfgsb200_solver_t *solver, int mode);
+int lbfgsb200_get_direction(const lbfgsb200_solver_t *solver);
+/* Process-wide default for solvers created afterwards, including the ones lbfgsb200_minimize_host* create
+ * internally; -1 = back to the environment's choice. */
+int lbfgsb200_set_default_direction(int mode);
+
 /* The iterative API  src/lbfgs.rs:443-566 */
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user);
 /* is_converged (src/lbfgs.rs:489-494): 1 = stop, 0 = continue; *stop_status gets the OK_* reason */

@@ -30,6 +30,7 @@ typedef std::vector<double> Vec;
 
 int g_mode = 0;  // reduction mode of the solve in flight (the oracle is single-threaded)
 int g_ls_variant = 0;  // experiment switch, see line_search_morethuente
+int g_dir_variant = 0; // 0 = the reference's two-loop recursion; 1 = "compact" direction, see two_loop_compact
 
 // ----- sums ---------------------------------------------------------------------------
 struct Acc {
@@ -532,9 +533,50 @@ struct IterationData {  // :607-627
     }
 };
 
+// NOT reference behaviour — the checker of the product's opt-in LBFGSB200_DIRECTION_COMPACT mode.  The same recursion
+// as :569-604 with the same element-wise operations in the same order, but the 2 * bound scalars alpha_j / beta_j are
+// derived from inner products of the UNMODIFIED vectors (s_i.y_j, y_i.y_j, s_i.d0, y_i.d0) instead of from the
+// vector as it is rewritten: s_j.q = s_j.d0 - sum_{i newer than j} alpha_i (s_j.y_i), and so on.  In exact arithmetic
+// both give the same numbers; in floating point the scalars differ by rounding only.
+int64_t two_loop_compact(std::vector<IterationData> &lm, double *d, int64_t n, double gamma, int64_t m, int64_t k,
+                         int64_t end) {
+    end = (end + 1) % m;
+    const int64_t bound = (m < k) ? m : k;
+    std::vector<int64_t> slot(bound);
+    for (int64_t t = 0, j = end; t < bound; ++t) { j = (j + m - 1) % m; slot[t] = j; }   // newest ... oldest
+    std::vector<double> sg(bound), yg(bound), SY(bound * bound), YY(bound * bound), alpha(bound), coef(bound);
+    for (int64_t a = 0; a < bound; ++a) {
+        sg[a] = vecdot(lm[slot[a]].s.data(), d, n);
+        yg[a] = vecdot(lm[slot[a]].y.data(), d, n);
+        for (int64_t b = 0; b < bound; ++b) {
+            SY[a * bound + b] = vecdot(lm[slot[a]].s.data(), lm[slot[b]].y.data(), n);
+            YY[a * bound + b] = vecdot(lm[slot[a]].y.data(), lm[slot[b]].y.data(), n);
+        }
+    }
+    for (int64_t a = 0; a < bound; ++a) {               // backward: newest -> oldest
+        double acc = sg[a];
+        for (int64_t i = 0; i < a; ++i) acc += -alpha[i] * SY[a * bound + i];
+        alpha[a] = acc / lm[slot[a]].ys;
+        lm[slot[a]].alpha = alpha[a];
+    }
+    for (int64_t a = bound - 1; a >= 0; --a) {          // forward: oldest -> newest
+        double acc = yg[a];
+        for (int64_t i = 0; i < bound; ++i) acc += -alpha[i] * YY[a * bound + i];
+        acc = acc * gamma;
+        for (int64_t i = bound - 1; i > a; --i) acc += coef[i] * SY[i * bound + a];
+        const double beta = acc / lm[slot[a]].ys;
+        coef[a] = alpha[a] - beta;
+    }
+    for (int64_t a = 0; a < bound; ++a) vecadd(d, lm[slot[a]].y.data(), -alpha[a], n);   // the element-wise passes of :589-599
+    vecscale(d, gamma, n);
+    for (int64_t a = bound - 1; a >= 0; --a) vecadd(d, lm[slot[a]].s.data(), coef[a], n);
+    return end;
+}
+
 // :569-604
 int64_t two_loop_recursion(std::vector<IterationData> &lm, double *d, int64_t n, double gamma,
                            int64_t m, int64_t k, int64_t end) {
+    if (g_dir_variant == 1) return two_loop_compact(lm, d, n, gamma, m, k, end);
     end = (end + 1) % m;
     int64_t j = end;
     int64_t bound = (m < k) ? m : k;
@@ -682,6 +724,8 @@ int oracle_minimize(const oracle_param_t *param, double *x, int64_t n, oracle_ev
     {
         const char *v = getenv("ORACLE_LS_VARIANT");
         g_ls_variant = (v && v[0] == '1') ? 1 : 0;
+        const char *w = getenv("ORACLE_DIRECTION_VARIANT");
+        g_dir_variant = (w && w[0] == '1') ? 1 : 0;
     }
 
     Owl owl;

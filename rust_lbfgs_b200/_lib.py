@@ -24,6 +24,7 @@ STATUS_NAMES = {
     -20: "ERR_CUDA", -21: "ERR_NCCL", -22: "ERR_STATE", -23: "ERR_UNSUPPORTED",
 }
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
+DIRECTION_TWO_LOOP, DIRECTION_COMPACT = 0, 1
 ABI_VERSION = 3
 FUSED_SUMS_OVER_RANKS = 1
 FUSED_COMMIT_SKIPS_GP = 2
@@ -137,6 +138,9 @@ def lib():
     _sig(L, "lbfgsb200_minimize_host", i32, [pp(Param), vp, i64, i32, vp, vp, vp, vp, pp(Report)])
     _sig(L, "lbfgsb200_minimize_host_ex", i32, [pp(Param), vp, i64, i64, i64, i32, vp, vp, vp, pp(FusedOps), vp, vp, pp(Report)])
     _sig(L, "lbfgsb200_set_fused_ops", i32, [vp, pp(FusedOps)])
+    _sig(L, "lbfgsb200_set_direction", i32, [vp, i32])
+    _sig(L, "lbfgsb200_get_direction", i32, [vp])
+    _sig(L, "lbfgsb200_set_default_direction", i32, [i32])
     _sig(L, "lbfgsb200_init_direction", i32, [vp, vp, i64, vp, pp(dbl)])
     _sig(L, "lbfgsb200_history_update", i32, [vp, vp, vp, vp, vp, vp, vp, i64, dbl, i32, vp, pp(dbl)])
     _sig(L, "lbfgsb200_damp_y", i32, [vp, vp, i64, dbl, dbl, dbl, vp, pp(i32)])

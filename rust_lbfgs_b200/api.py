@@ -171,6 +171,7 @@ class Lbfgs:
         self._comm = None
         self._shard = None  # (n_global, global_offset)
         self._fused_trial = True
+        self._direction = None  # None: the library's default (two-loop unless LBFGSB200_DIRECTION=compact)
 
     # -- src/lbfgs.rs:194-383, in source order ------------------------------------------------
     def with_epsilon(self, epsilon):
@@ -281,6 +282,18 @@ class Lbfgs:
         self._fused_trial = fused
         return self
 
+    def with_direction(self, mode):
+        """How H.(-g) (src/lbfgs.rs:569-604) is formed.  "two_loop" (default): the reference's recursion, one fused
+        pass per trip.  "compact": the same element-wise operations in the same order, with the 2 * min(m, k) scalars
+        alpha_j / beta_j derived from inner products of the unmodified ring vectors (kept on the device across
+        iterations): two passes over the ring instead of 2 * min(m, k) dependent ones, (4 b + 4) V of traffic instead
+        of (8 b - 1) V, and one all-reduce per iteration on N GPUs.  Results differ from the reference's by rounding
+        in those scalars only (include/lbfgsb200.h).  m <= 32."""
+        table = {"two_loop": _lib.DIRECTION_TWO_LOOP, "compact": _lib.DIRECTION_COMPACT}
+        _require(mode in table, "Invalid direction mode.")
+        self._direction = table[mode]
+        return self
+
     def with_shard(self, comm, n_global, global_offset):
         """This rank's x is elements [global_offset, global_offset + len(x)) of an n_global vector;
         `comm` is a rust_lbfgs_b200.dist.Comm (one NCCL rank per GPU)."""
@@ -341,9 +354,15 @@ class Lbfgs:
             cb = PROGRESS_FN(on_progress)
             cbp = C.cast(cb, C.c_void_p)
         rep = _lib.Report()
-        st = L.lbfgsb200_minimize_host_ex(C.byref(self.param), ptr, n, n_global, goff, device, comm, ev.fn, ev.user,
-                                          C.byref(ev.fused_ops) if ev.fused_ops is not None else None, cbp, None,
-                                          C.byref(rep))
+        if self._direction is not None:   # the solver is created inside the call: it takes the process default
+            L.lbfgsb200_set_default_direction(self._direction)
+        try:
+            st = L.lbfgsb200_minimize_host_ex(C.byref(self.param), ptr, n, n_global, goff, device, comm, ev.fn, ev.user,
+                                              C.byref(ev.fused_ops) if ev.fused_ops is not None else None, cbp, None,
+                                              C.byref(rep))
+        finally:
+            if self._direction is not None:
+                L.lbfgsb200_set_default_direction(-1)
         report = _report_from_c(rep)
         report.status = st
         if st == -5:
@@ -365,6 +384,7 @@ class LbfgsState:
         self._L = _lib.lib()
         ptr, n, device = _ptr_n_device(x)
         self._device = device
+        self._n = n
         self._x_owner = x
         self._solver = _make_solver(builder, n, device)
         self._ev = _Evaluate(evaluate, device, builder.param.reduction, builder._fused_trial, builder._comm)
@@ -398,6 +418,10 @@ class LbfgsState:
         st = self._L.lbfgsb200_finish(self._solver)
         if st != 0:
             raise LbfgsError(st, self._L.lbfgsb200_last_error(self._solver).decode())
+
+    def direction(self):
+        """The current search direction d (solver-owned device memory, aliased — clone() to keep it)."""
+        return device_view(self._L.lbfgsb200_direction(self._solver), self._n, self._device)
 
     # instrumentation
     def profile_enable(self, timing=True, kinds=None):
@@ -464,6 +488,14 @@ def _make_solver(builder, n, device):
         raise ValueError("invalid L-BFGS parameter (the reference would panic)")
     if st != 0:
         raise LbfgsError(st, "lbfgsb200_create failed (no CUDA device? rust_lbfgs_b200 has no CPU fallback)")
+    if builder._direction is not None:
+        st = L.lbfgsb200_set_direction(out, builder._direction)
+        if st != 0:
+            msg = L.lbfgsb200_last_error(out).decode()
+            L.lbfgsb200_destroy(out)
+            if st == -5:
+                raise ValueError(msg)
+            raise LbfgsError(st, msg)
     return out
 
 

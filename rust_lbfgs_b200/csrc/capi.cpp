@@ -140,6 +140,14 @@ int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_op
     S(solver)->set_fused_ops(ops);
     return 0;
 }
+int lbfgsb200_set_direction(lbfgsb200_solver_t *solver, int mode) {
+    if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
+    return S(solver)->set_direction(mode);
+}
+int lbfgsb200_set_default_direction(int mode) { return lb::set_default_direction(mode); }
+int lbfgsb200_get_direction(const lbfgsb200_solver_t *solver) {
+    return solver ? S(solver)->direction_mode() : LBFGSB200_ERR_INVALID_PARAM;
+}
 int lbfgsb200_build(lbfgsb200_solver_t *solver, double *x_dev, lbfgsb200_eval_fn eval, void *eval_user) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
     return S(solver)->build(x_dev, eval, eval_user);

@@ -82,4 +82,17 @@ cudaError_t launch_two_loop_small(const Launch &L, int device, int64_t n, int m,
                                   double *out, bool owl, int64_t start, int64_t end, int64_t goff, double max_step,
                                   bool constrain, double *step_out);
 
+
+// The opt-in compact search direction (compact.cu; src/lbfgs.rs:569-604 with the 2 * bound scalars derived from inner
+// products of the unmodified ring vectors): pass A for the t-th newest slots given by s[] / y[] (cnt <=
+// kCompactGroupMax older slots per launch, 5 sums each; `newdot` adds {y_new.d0, y_new.y_new}), the scalar recursions,
+// and pass B (d written once; out = {d.d before projection, g.d | pg.d, d.d after}).
+void launch_gram(const Launch &L, const double *s_new, const double *y_new, const double *src, const double *const *s,
+                 const double *const *y, int cnt, bool newdot, int64_t n, double *wide_partials, double *out);
+void launch_compact_solve(const Launch &L, int m, int bound, int slot_new, const double *sums, const double *hist,
+                          double *SY, double *YY, double *ys_dev, double *coefs);
+void launch_direction(const Launch &L, double *d, const double *src, const double *ring, int64_t stride, int64_t n, int m,
+                      int bound, int slot_new, const double *coefs, bool owl, int64_t start, int64_t end, int64_t goff,
+                      double *out);
+
 }  // namespace lb

@@ -1,6 +1,7 @@
 // solver.cpp — see solver.h.  Compiled by nvcc as host code with -ffp-contract=off.
 #include "solver.h"
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -28,6 +29,10 @@ struct DbgTimer {  // LBFGSB200_DEBUG_TIMING=1: wall time of the host-side phase
     }
 };
 }  // namespace
+
+namespace {
+std::atomic<int> g_default_direction{-1};   // -1: not set, the environment decides
+}
 
 int query_device(int device, DeviceInfo *out) {
     int count = 0;
@@ -181,6 +186,7 @@ Solver::~Solver() {
     for (auto &p : pending_) { event_pool_.push_back(p.a); event_pool_.push_back(p.b); }
     for (auto e : event_pool_) cudaEventDestroy(e);
     tm.lap("destroy: events");
+    if (cmp_block_) { cudaStreamSynchronize(stream_); cudaFree(cmp_block_); }
     if (arena_) {
         if (arena_pooled_) cudaFreeAsync(arena_, stream_);
         else cudaFree(arena_);
@@ -314,6 +320,48 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     small_enabled_ = env_int("LBFGSB200_SMALL", 1) != 0;
     speculate_ = env_int("LBFGSB200_SPECULATE", 1) != 0;
     ring_stride_ = vec_bytes / (int64_t)sizeof(double);
+    // process-wide default (lbfgsb200_set_default_direction, else LBFGSB200_DIRECTION=compact); lbfgsb200_set_direction wins
+    int dflt = g_default_direction.load();
+    if (dflt < 0) {
+        const char *dm = getenv("LBFGSB200_DIRECTION");
+        dflt = (dm && strcmp(dm, "compact") == 0) ? LBFGSB200_DIRECTION_COMPACT : LBFGSB200_DIRECTION_TWO_LOOP;
+    }
+    if (dflt == LBFGSB200_DIRECTION_COMPACT && m_ <= kCompactMaxM) return set_direction(LBFGSB200_DIRECTION_COMPACT);
+    return 0;
+}
+
+int set_default_direction(int mode) {
+    if (mode != -1 && mode != LBFGSB200_DIRECTION_TWO_LOOP && mode != LBFGSB200_DIRECTION_COMPACT) return LBFGSB200_ERR_INVALID_PARAM;
+    g_default_direction.store(mode);
+    return 0;
+}
+
+int Solver::set_direction(int mode) {
+    if (mode != LBFGSB200_DIRECTION_TWO_LOOP && mode != LBFGSB200_DIRECTION_COMPACT)
+        return fail(LBFGSB200_ERR_INVALID_PARAM, "unknown direction mode");
+    if (!arena_) return fail(LBFGSB200_ERR_STATE, "solver not initialised");
+    if (built_ && k_ > 1) return fail(LBFGSB200_ERR_STATE, "the direction mode cannot change in the middle of a solve");
+    if (mode == LBFGSB200_DIRECTION_TWO_LOOP) { compact_ = false; return 0; }
+    if (m_ > kCompactMaxM) return fail(LBFGSB200_ERR_INVALID_PARAM, "the compact direction supports m <= 32");
+    if (!cmp_block_) {
+        cudaError_t e = cudaSetDevice(dev_.device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        const size_t mm = (size_t)round_up(m_ * m_, 32);
+        const size_t nsums = (size_t)round_up(5 * m_ + 8, 32);
+        const size_t ncoef = (size_t)round_up(1 + 2 * kCompactMaxM, 32);
+        const size_t npart = (size_t)(5 * kCompactGroupMax + 2) * (size_t)ws_.stride;
+        const size_t total = 2 * mm + nsums + ncoef + npart;
+        e = cudaMalloc((void **)&cmp_block_, total * sizeof(double));
+        if (e != cudaSuccess) { cmp_block_ = nullptr; return cuda_fail(e, "cudaMalloc(compact direction state)"); }
+        e = cudaMemsetAsync(cmp_block_, 0, total * sizeof(double), stream_);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(compact direction state)");
+        cmp_sy_ = cmp_block_;
+        cmp_yy_ = cmp_sy_ + mm;
+        cmp_sums_ = cmp_yy_ + mm;
+        cmp_coefs_ = cmp_sums_ + nsums;
+        cmp_partials_ = cmp_coefs_ + ncoef;
+    }
+    compact_ = true;
     return 0;
 }
 
@@ -681,6 +729,47 @@ int Solver::enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, i
     return 0;
 }
 
+// The compact direction (compact.cu): the recursion of src/lbfgs.rs:569-604 with its 2 * bound scalars derived from
+// inner products of the unmodified ring vectors — two passes over the ring instead of 2 * bound dependent ones.
+int Solver::compact_direction(const Launch &L, int64_t bound, int *so_last) {
+    const double vbytes = 8.0 * (double)n_;
+    const int b = (int)bound, e = (int)end_, m = (int)m_;
+    const int nold = b - 1;
+    const double *src = owl_ ? pg_ : gbuf_[cur_g_];   // d0 = -g | -pg, core.rs:95-101
+    auto slot_of = [&](int t) { return (e + m - t) % m; };   // the t-th newest pair
+    if (nold == 0) {
+        prof_begin(LBFGSB200_K_BACKWARD);
+        launch_gram(L, S_[e], Y_[e], src, nullptr, nullptr, 0, true, n_, cmp_partials_, cmp_sums_);
+        prof_end(LBFGSB200_K_BACKWARD, 2.0 * vbytes);
+    } else {
+        const int groups = (nold + kCompactGroupMax - 1) / kCompactGroupMax;
+        const int per = (nold + groups - 1) / groups;
+        for (int t0 = 1; t0 <= nold; t0 += per) {
+            const int cnt = (nold - t0 + 1 < per) ? (nold - t0 + 1) : per;
+            const double *sp[kCompactGroupMax], *yp[kCompactGroupMax];
+            for (int c = 0; c < cnt; ++c) { sp[c] = S_[slot_of(t0 + c)]; yp[c] = Y_[slot_of(t0 + c)]; }
+            const bool newdot = t0 + cnt > nold;      // the last group also sums y_new.d0 and y_new.y_new
+            prof_begin(LBFGSB200_K_BACKWARD);
+            launch_gram(L, S_[e], Y_[e], src, sp, yp, cnt, newdot, n_, cmp_partials_, cmp_sums_ + 5 * (t0 - 1));
+            prof_end(LBFGSB200_K_BACKWARD, (3.0 + 2.0 * cnt) * vbytes);
+        }
+    }
+    if (comm_ && comm_size(comm_) > 1) {   // one all-reduce for every sum of the iteration (same bits on every rank)
+        prof_.allreduces += 1;
+        const int rc = comm_allreduce_sum(comm_, cmp_sums_, 5 * nold + 2, stream_);
+        if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    }
+    launch_compact_solve(L, m, b, e, cmp_sums_, slot(SLOT_HIST), cmp_sy_, cmp_yy_, ys_dev_, cmp_coefs_);
+    prof_begin(LBFGSB200_K_FORWARD);
+    launch_direction(L, d_, src, S_[0], ring_stride_, n_, m, b, e, cmp_coefs_, owl_, owl_start_, owl_end_, goff_,
+                     slot(SLOT_LOOP_A));
+    prof_end(LBFGSB200_K_FORWARD, (2.0 * b + 2.0) * vbytes);
+    const int rc = reduce_across_ranks(SLOT_LOOP_A, 3);
+    if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    *so_last = SLOT_LOOP_A;
+    return 0;
+}
+
 // The launch-bound regime: all 2 * bound trips in one cluster-persistent kernel (small.cu).  One GPU, tree
 // reductions; anything it cannot take (or a refused cluster launch) goes to the multi-kernel chain.
 bool Solver::small_eligible() const {
@@ -865,7 +954,8 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     rc = enqueue_history(L, xp, gp, stp_eval);
     if (rc != 0) return rc;
     bool small_ran = false;
-    if (small_eligible()) { rc = two_loop_small(L, bound, &so_last); small_ran = small_enabled_; }
+    if (compact_) rc = compact_direction(L, bound, &so_last);
+    else if (small_eligible()) { rc = two_loop_small(L, bound, &so_last); small_ran = small_enabled_; }
     else if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
     else rc = enqueue_two_loop(L, gp, bound, &so_last);
     if (rc != 0) return rc;

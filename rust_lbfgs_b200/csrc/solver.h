@@ -42,6 +42,8 @@ struct DeviceInfo {
                                    // (LBFGSB200_TRIAL_BLOCKS_PER_SM)
 };
 int query_device(int device, DeviceInfo *out);
+// process-wide default direction mode of solvers created afterwards (-1: back to the environment's choice)
+int set_default_direction(int mode);
 // returns the pages cached by the solver arenas' memory pool to the driver
 int trim_pool(int device);
 // allocates the level-2 reduction workspace for `info`
@@ -78,6 +80,10 @@ class Solver {
     }
     void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; spec_.valid = false; }
 
+    // LBFGSB200_DIRECTION_*: how the search direction is formed (before build(); compact needs m <= kCompactMaxM)
+    int set_direction(int mode);
+    int direction_mode() const { return compact_ ? LBFGSB200_DIRECTION_COMPACT : LBFGSB200_DIRECTION_TWO_LOOP; }
+
     // timing: 0 = off, 1 = every kernel kind, otherwise a mask: bit (1 + kind) times LBFGSB200_K_<kind> only
     void profile_enable(int timing) { timing_ = timing != 0; timing_mask_ = (timing == 1) ? ~0u : ((unsigned)timing >> 1); }
     void profile_get(lbfgsb200_profile_t *out);
@@ -113,6 +119,8 @@ class Solver {
     int enqueue_history(const Launch &L, const double *xp, const double *gp, double step_eval);
     // (+ damping) + two-loop of one iteration, enqueued on L.stream; *so_last = slot of the final dots
     int enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, int *so_last);
+    // the compact direction (compact.cu): pass A + scalar recursions + pass B instead of the 2 * bound trips
+    int compact_direction(const Launch &L, int64_t bound, int *so_last);
     bool small_eligible() const;   // the cluster-persistent two-loop kernel (small.cu) applies
     int two_loop_small(const Launch &L, int64_t bound, int *so_last);
     bool graph_eligible(int64_t bound) const;
@@ -186,6 +194,11 @@ class Solver {
     bool small_enabled_ = true;      // LBFGSB200_SMALL=0 disables; cleared if the cluster launch is refused
     int64_t ring_stride_ = 0;        // doubles between consecutive ring vectors (S_0, Y_0, S_1, ...)
     int64_t graph_replays_ = 0;
+
+    // compact direction: S^T Y, Y^T Y (m x m each), this iteration's sums, the coefficients, wide reduction partials
+    bool compact_ = false;
+    double *cmp_block_ = nullptr;
+    double *cmp_sy_ = nullptr, *cmp_yy_ = nullptr, *cmp_sums_ = nullptr, *cmp_coefs_ = nullptr, *cmp_partials_ = nullptr;
 
     // profile
     bool timing_ = false;

@@ -57,6 +57,12 @@ struct PeerCtx {
     unsigned int *fault;           // communicator-owned device word, set when a peer did not answer in time
 };
 
+// The opt-in compact search direction (compact.cu): history depth it supports and older ring slots per pass-A launch
+// (5 running sums each, kept in registers).
+constexpr int kCompactMaxM = 32;
+constexpr int kCompactGroupMax = 5;
+constexpr int kCompactSplitDefault = 0;   // ring vectors per sub-pass of pass B beyond bound 8 (0 = one pass); tuned on B200
+
 // Per-solver reduction workspace in HBM.
 struct ReduceWs {
     double *partials;      // [kMaxAcc][stride]

@@ -204,6 +204,9 @@ class Lbfgs {
     }
     // false: line-search trials as K1 + evaluate + K2 even if the objective offers probe + commit / a fused trial
     Lbfgs &with_fused_trial(bool fused) { fused_ = fused; return *this; }
+    // LBFGSB200_DIRECTION_COMPACT: the direction from two passes over the ring instead of 2 * min(m, k) dependent trips
+    // (same element-wise operations; alpha_j / beta_j from inner products of the unmodified ring vectors).  m <= 32.
+    Lbfgs &with_direction(int mode) { direction_ = mode; return *this; }
 
     // minimize, src/lbfgs.rs:399-421.  x_dev: n doubles of device memory, updated in place.
     Report minimize(double *x_dev, int64_t n, DeviceEvaluate evaluate, ProgressFn progress = nullptr) const {
@@ -257,6 +260,13 @@ class Lbfgs {
             int rc = lbfgsb200_create(&b.p_, n, ng, b.goff_, b.device_, b.stream_, b.comm_, &s);
             if (rc == LBFGSB200_ERR_INVALID_PARAM) throw std::invalid_argument("invalid L-BFGS parameter");
             if (rc != 0) throw Error(rc, "lbfgsb200_create failed (no CUDA device? there is no CPU fallback)");
+            if (b.direction_ >= 0 && (rc = lbfgsb200_set_direction(s, b.direction_)) != 0) {
+                const std::string msg = lbfgsb200_last_error(s);
+                lbfgsb200_destroy(s);
+                s = nullptr;
+                if (rc == LBFGSB200_ERR_INVALID_PARAM) throw std::invalid_argument(msg);
+                throw Error(rc, msg);
+            }
         }
         Handle(const Handle &) = delete;
         Handle &operator=(const Handle &) = delete;
@@ -288,6 +298,7 @@ class Lbfgs {
     lbfgsb200_comm_t *comm_ = nullptr;
     int64_t n_global_ = 0, goff_ = 0;
     bool fused_ = true;
+    int direction_ = -1;   // < 0: the library's default
 };
 
 // LbfgsState, src/lbfgs.rs:425-566

@@ -27,6 +27,8 @@ pub const LBFGSB200_LS_BACKTRACKING_STRONG_WOLFE: i64 = 3;
 
 pub const LBFGSB200_REDUCE_TREE: i64 = 0;
 pub const LBFGSB200_REDUCE_SEQUENTIAL: i64 = 1;
+pub const LBFGSB200_DIRECTION_TWO_LOOP: c_int = 0;
+pub const LBFGSB200_DIRECTION_COMPACT: c_int = 1;
 
 /// `lbfgsb200_param_t`: LbfgsParam + LineSearch + Orthantwise flattened (8-byte fields only).
 #[repr(C)]
@@ -156,6 +158,9 @@ extern "C" {
                               progress: lbfgsb200_progress_fn, progress_user: *mut c_void, report: *mut lbfgsb200_report_t) -> c_int;
     pub fn lbfgsb200_set_trial_evaluate(solver: *mut lbfgsb200_solver_t, f: lbfgsb200_trial_eval_fn, user: *mut c_void) -> c_int;
     pub fn lbfgsb200_set_fused_ops(solver: *mut lbfgsb200_solver_t, ops: *const lbfgsb200_fused_ops_t) -> c_int;
+    pub fn lbfgsb200_set_direction(solver: *mut lbfgsb200_solver_t, mode: c_int) -> c_int;
+    pub fn lbfgsb200_get_direction(solver: *const lbfgsb200_solver_t) -> c_int;
+    pub fn lbfgsb200_set_default_direction(mode: c_int) -> c_int;
     pub fn lbfgsb200_build(solver: *mut lbfgsb200_solver_t, x_dev: *mut f64, eval: lbfgsb200_eval_fn, eval_user: *mut c_void) -> c_int;
     pub fn lbfgsb200_is_converged(solver: *mut lbfgsb200_solver_t, stop_status: *mut c_int) -> c_int;
     pub fn lbfgsb200_propagate(solver: *mut lbfgsb200_solver_t, progress_out: *mut lbfgsb200_progress_t) -> c_int;

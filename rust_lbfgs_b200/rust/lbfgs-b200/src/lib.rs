@@ -186,11 +186,11 @@ unsafe extern "C" fn progress_tramp<G: FnMut(&Progress) -> bool>(user: *mut c_vo
 
 /// The builder (src/lbfgs.rs:179-384); `param` is private like the reference's.
 #[derive(Clone, Debug)]
-pub struct Lbfgs { param: sys::lbfgsb200_param_t, fused_trial: bool, shard: Option<(*mut sys::lbfgsb200_comm_t, i64, i64)> }
+pub struct Lbfgs { param: sys::lbfgsb200_param_t, fused_trial: bool, compact: Option<bool>, shard: Option<(*mut sys::lbfgsb200_comm_t, i64, i64)> }
 impl Default for Lbfgs {
     fn default() -> Self {
         let mut p = std::mem::MaybeUninit::<sys::lbfgsb200_param_t>::zeroed();
-        unsafe { sys::lbfgsb200_param_default(p.as_mut_ptr()); Self { param: p.assume_init(), fused_trial: true, shard: None } }
+        unsafe { sys::lbfgsb200_param_default(p.as_mut_ptr()); Self { param: p.assume_init(), fused_trial: true, compact: None, shard: None } }
     }
 }
 /// Create a default LBFGS optimizer (src/lib.rs:74-76).
@@ -234,6 +234,10 @@ impl Lbfgs {
     pub fn with_sequential_reduction(mut self, on: bool) -> Self { self.param.reduction = on as i64; self }
     /// false: line-search trials as K1 + evaluate + K2 even if the objective offers probe + commit / a fused trial.
     pub fn with_fused_trial(mut self, on: bool) -> Self { self.fused_trial = on; self }
+    /// true: the search direction from two passes over the ring (alpha_j / beta_j derived from inner products of the
+    /// unmodified ring vectors, include/lbfgsb200.h: LBFGSB200_DIRECTION_COMPACT) instead of the reference's 2 * min(m, k)
+    /// dependent trips; same element-wise operations, scalars equal up to rounding.  m <= 32.
+    pub fn with_compact_direction(mut self, on: bool) -> Self { self.compact = Some(on); self }
     /// This rank's `x` is elements `[global_offset, global_offset + x.len())` of an `n_global` vector (one process per GPU).
     pub fn with_shard(mut self, comm: &Comm, n_global: usize, global_offset: usize) -> Self {
         self.shard = Some((comm.handle, n_global as i64, global_offset as i64)); self
@@ -248,9 +252,12 @@ impl Lbfgs {
         if !comm.is_null() { eval_fn.attach_comm(comm)?; }
         let ops = if self.fused_trial { eval_fn.fused_ops() } else { None };
         let mut rep = sys::lbfgsb200_report_t::default();
+        // the solver is created inside the call: it takes the process-wide default
+        if let Some(on) = self.compact { unsafe { sys::lbfgsb200_set_default_direction(on as c_int); } }
         let st = unsafe { sys::lbfgsb200_minimize_host_ex(&self.param, x.as_mut_ptr(), x.len() as i64, n_global, goff, device, comm,
                                                           eval.0, eval.1, ops.as_ref().map_or(std::ptr::null(), |o| o as *const _),
                                                           Some(progress_tramp::<G>), &mut prgr_fn as *mut G as *mut c_void, &mut rep) };
+        if self.compact.is_some() { unsafe { sys::lbfgsb200_set_default_direction(-1); } }
         if st < 0 { bail!("minimize failed with status {st}") }
         Ok(Report { fx: rep.fx, xnorm: rep.xnorm, gnorm: rep.gnorm, neval: rep.neval as usize })
     }
@@ -280,6 +287,10 @@ impl Lbfgs {
         let (comm, n_global, goff) = self.shard.unwrap_or((std::ptr::null_mut(), n as i64, 0));
         let rc = unsafe { sys::lbfgsb200_create(&self.param, n as i64, n_global, goff, device, std::ptr::null_mut(), comm, &mut solver) };
         if rc != 0 { bail!("lbfgsb200_create failed with status {rc} (no CUDA device? there is no CPU fallback)") }
+        if let Some(on) = self.compact {
+            let rc = unsafe { sys::lbfgsb200_set_direction(solver, on as c_int) };
+            if rc != 0 { unsafe { sys::lbfgsb200_destroy(solver) }; bail!("lbfgsb200_set_direction failed with status {rc} (the compact direction needs m <= 32)") }
+        }
         let eval = eval_fn.raw().unwrap_or((Some(eval_tramp::<E>), eval_fn as *mut E as *mut c_void));
         if !comm.is_null() { eval_fn.attach_comm(comm)?; }
         if self.fused_trial {

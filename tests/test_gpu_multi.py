@@ -62,6 +62,11 @@ CASES = [
     dict(n=1000, kw={"with_orthantwise": (0.5, 100, 900)}),
     dict(n=1000, kw={"with_linesearch_algorithm": ("BacktrackingStrongWolfe",), "with_damping": (True,)}),
     dict(n=(1 << 22) + 6, kw={"with_max_iterations": (12,), "with_m": (3,)}),
+    # the compact search direction: one all-reduce of the iteration's 5b - 3 sums instead of 2b exchanges
+    dict(n=100002, kw={"with_max_iterations": (40,), "with_direction": ("compact",)}),
+    dict(n=1000, kw={"with_m": (20,), "with_direction": ("compact",)}),
+    dict(n=1000, kw={"with_orthantwise": (0.5, 100, 900), "with_direction": ("compact",)}),
+    dict(n=(1 << 22) + 6, kw={"with_max_iterations": (12,), "with_m": (3,), "with_direction": ("compact",)}),
 ]
 
 
