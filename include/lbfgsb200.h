@@ -160,6 +160,18 @@ typedef int (*lbfgsb200_commit_fn)(void *user, const double *xp_dev, const doubl
                                    double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                    double *y_dev, int64_t n_local, void *stream, double *out_dev);
 
+/* Optional: the commit fused with pass A of the compact search direction (lbfgsb200_set_direction).  Everything the
+ * commit does, plus — from the registers that hold the new pair s = x - xp, y = g - gp and the new gradient g — the
+ * inner products with n_old <= 5 older ring pairs (HOST arrays of device pointers s_old_dev[k], y_old_dev[k]):
+ *   gram_out_dev[5 k + 0..4] = { s_k.d0, y_k.d0, s.y_k, s_k.y, y.y_k },  newdot_out_dev[0..1] = { y.d0, y.y },  d0 = -g
+ * (partials of this rank; never combined with LBFGSB200_FUSED_SUMS_OVER_RANKS — return LBFGSB200_ERR_UNSUPPORTED and
+ * the solver runs commit + pass A separately, as it does on N > 1 GPUs, with Powell damping and for OWL-QN). */
+typedef int (*lbfgsb200_commit_gram_fn)(void *user, const double *xp_dev, const double *d_dev, const double *gp_dev,
+                                        double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
+                                        double *y_dev, const double *const *s_old_dev, const double *const *y_old_dev,
+                                        int n_old, int64_t n_local, void *stream, double *out_dev, double *gram_out_dev,
+                                        double *newdot_out_dev);
+
 /* What an objective offers beyond lbfgsb200_eval_fn.  Unused entries are NULL.  probe needs commit. */
 #define LBFGSB200_FUSED_SUMS_OVER_RANKS 1  /* the callbacks leave sums over ALL ranks in out_dev (the built-in
                                               objectives do, in their kernels' epilogue, once
@@ -173,7 +185,10 @@ typedef struct lbfgsb200_fused_ops {
     lbfgsb200_commit_fn commit;         /* accepted point + history update */
     void *user;
     int64_t flags;                      /* LBFGSB200_FUSED_* */
+    lbfgsb200_commit_gram_fn commit_gram;  /* commit + pass A of the compact direction (struct_size tells whether the
+                                              caller's struct has this field: LBFGSB200_FUSED_OPS_SIZE_V1 = without) */
 } lbfgsb200_fused_ops_t;
+#define LBFGSB200_FUSED_OPS_SIZE_V1 48
 
 /* Progress  src/core.rs:221-250; x/gx are device pointers to this rank's shard */
 typedef struct lbfgsb200_progress {
@@ -443,6 +458,12 @@ int  lbfgsb200_objective_probe(void *objective, const double *xp_dev, const doub
 int  lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                 double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                 double *y_dev, int64_t n_local, void *stream, double *out_dev);
+/* the lbfgsb200_commit_gram_fn of the built-in objectives (Rosenbrock on one GPU; LBFGSB200_ERR_UNSUPPORTED otherwise) */
+int  lbfgsb200_objective_commit_gram(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
+                                     double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
+                                     double *y_dev, const double *const *s_old_dev, const double *const *y_old_dev,
+                                     int n_old, int64_t n_local, void *stream, double *out_dev, double *gram_out_dev,
+                                     double *newdot_out_dev);
 int  lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fused_ops_t *out);
 
 /* ---- line-search state machines (pure host code; exposed so the scalar logic can be checked

@@ -80,7 +80,7 @@ COMMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
 class FusedOps(C.Structure):
     """lbfgsb200_fused_ops_t: what an objective offers beyond evaluate (function pointers as void*)."""
     _fields_ = [("struct_size", C.c_int64), ("trial", C.c_void_p), ("probe", C.c_void_p), ("commit", C.c_void_p),
-                ("user", C.c_void_p), ("flags", C.c_int64)]
+                ("user", C.c_void_p), ("flags", C.c_int64), ("commit_gram", C.c_void_p)]
 
 _lib = None
 

@@ -135,9 +135,15 @@ int lbfgsb200_set_trial_evaluate(lbfgsb200_solver_t *solver, lbfgsb200_trial_eva
 }
 int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_ops_t *ops) {
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
-    if (ops && (ops->struct_size != (int64_t)sizeof(lbfgsb200_fused_ops_t) || (ops->probe && !ops->commit)))
+    if (!ops) { S(solver)->set_fused_ops(nullptr); return 0; }
+    // a caller built against the header before `commit_gram` was appended passes the shorter struct
+    if ((ops->struct_size != (int64_t)sizeof(lbfgsb200_fused_ops_t) && ops->struct_size != LBFGSB200_FUSED_OPS_SIZE_V1) ||
+        (ops->probe && !ops->commit))
         return LBFGSB200_ERR_INVALID_PARAM;
-    S(solver)->set_fused_ops(ops);
+    lbfgsb200_fused_ops_t full{};
+    memcpy(&full, ops, (size_t)ops->struct_size);
+    full.struct_size = (int64_t)sizeof(lbfgsb200_fused_ops_t);
+    S(solver)->set_fused_ops(&full);
     return 0;
 }
 int lbfgsb200_set_direction(lbfgsb200_solver_t *solver, int mode) {

@@ -47,6 +47,7 @@ struct Objective {
     Comm *comm = nullptr;            // GLM: rows of X sharded, f and g summed over ranks; LJ: atoms sharded
     std::vector<int64_t> offsets;    // LJ: element offsets of every rank's shard (nranks + 1)
     double *xall = nullptr;          // LJ: all positions, gathered before every evaluation
+    double *wide_partials = nullptr; // Rosenbrock commit fused with pass A of the compact direction: 32 sums per CTA
 };
 
 // ---- Rosenbrock ------------------------------------------------------------------------------
@@ -189,6 +190,79 @@ k_rosenbrock_commit(RosenCommitOp<S, RECOMPUTE_GP> op, int64_t n, ReduceWs ws, d
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     stream_pairs<5, kUh>(n, op, acc);
     grid_reduce<5>(acc, ws, out);
+}
+
+// The commit fused with pass A of the compact search direction (lbfgsb200_commit_gram_fn; csrc/compact.cu): the new
+// pair (s, y) and the new gradient are in registers here, so their inner products with G older ring pairs — the new
+// row and column of S^T Y, Y^T Y and S^T d0, Y^T d0 with d0 = -g — are formed before they are stored: 2R 4W + 2G R in
+// one pass instead of 2R 4W followed by (3 + 2G) R.  Sums: [0, 5) the history sums of the commit, then per older pair
+// {s_k.d0, y_k.d0, s.y_k, s_k.y, y.y_k}, then {y.d0, y.y}.  Same element-wise arithmetic as the commit and as k_gram.
+template <bool S, int G>
+struct RosenCommitGramOp {
+    const double *xp, *d;
+    double *x, *g, *s, *y;
+    double step, nstep;
+    const double *so[G > 0 ? G : 1], *yo[G > 0 ? G : 1];
+    static constexpr int kAcc = 5 + 5 * G + 2;
+    struct Regs { double2 xp, d; double2 so[G > 0 ? G : 1], yo[G > 0 ? G : 1]; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const {
+        r.xp = ld2<S>(xp, i);
+        r.d = ld2<S>(d, i);
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            r.so[k] = ld2<S>(so[k], i);
+            r.yo[k] = ld2<S>(yo[k], i);
+        }
+    }
+    __device__ __forceinline__ void gram(double sn, double yn, double gn, const double *sk, const double *yk, double (&acc)[kAcc]) const {
+        const double ng = -gn;                              // d0 = -g, core.rs:95-101
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            acc[5 + 5 * k + 0] += sk[k] * ng;
+            acc[5 + 5 * k + 1] += yk[k] * ng;
+            acc[5 + 5 * k + 2] += sn * yk[k];
+            acc[5 + 5 * k + 3] += sk[k] * yn;
+            acc[5 + 5 * k + 4] += yn * yk[k];
+        }
+        acc[5 + 5 * G + 0] += yn * ng;
+        acc[5 + 5 * G + 1] += yn * yn;
+    }
+    __device__ __forceinline__ void apply(Regs &r, int64_t i, double (&acc)[kAcc]) const {
+        double2 xo, o, sn, yn, gp;
+        rosen_pair(r.xp.x, r.xp.y, gp);                     // gp recomputed from xp (see RosenCommitOp)
+        xo.x = r.xp.x + step * r.d.x;                       // core.rs:156-157
+        xo.y = r.xp.y + step * r.d.y;
+        rosen_pair(xo.x, xo.y, o);
+        double (&h)[5] = reinterpret_cast<double (&)[5]>(acc);
+        history_elem<true, false>(xo.x, r.xp.x, o.x, gp.x, 0.0, nstep, sn.x, yn.x, h);
+        history_elem<true, false>(xo.y, r.xp.y, o.y, gp.y, 0.0, nstep, sn.y, yn.y, h);
+        double sx[G > 0 ? G : 1], yx[G > 0 ? G : 1], sy[G > 0 ? G : 1], yy[G > 0 ? G : 1];
+#pragma unroll
+        for (int k = 0; k < G; ++k) { sx[k] = r.so[k].x; yx[k] = r.yo[k].x; sy[k] = r.so[k].y; yy[k] = r.yo[k].y; }
+        gram(sn.x, yn.x, o.x, sx, yx, acc);
+        gram(sn.y, yn.y, o.y, sy, yy, acc);
+        st2<S>(x, i, xo);
+        st2<S>(g, i, o);
+        st2<S>(s, i, sn);
+        st2<S>(y, i, yn);
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[kAcc]) const {}
+};
+#ifndef LB_CG_U
+#define LB_CG_U 2        // pairs per thread per tile ...
+#endif
+#ifndef LB_CG_BLOCKS
+#define LB_CG_BLOCKS 1   // ... and resident CTAs per SM of the fused commit + pass A kernel (tuned: profiles/r02_tuning.md)
+#endif
+template <bool S, int G>
+__global__ void __launch_bounds__(kThreads, LB_CG_BLOCKS)
+k_rosenbrock_commit_gram(RosenCommitGramOp<S, G> op, int64_t n, ReduceWs ws, double *hist, double *gram_out, double *newdot_out) {
+    constexpr int kAcc = RosenCommitGramOp<S, G>::kAcc;
+    double acc[kAcc];
+#pragma unroll
+    for (int a = 0; a < kAcc; ++a) acc[a] = 0.0;
+    stream_pairs<kAcc, LB_CG_U>(n, op, acc);
+    grid_reduce_split<kAcc>(acc, ws, hist, 5, gram_out, 5 * G, newdot_out);
 }
 
 // ---- Booth -----------------------------------------------------------------------------------
@@ -913,6 +987,59 @@ int commit_impl(Objective *o, const double *xp, const double *d, const double *g
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
+template <int G>
+int commit_gram_launch(Objective *o, const double *xp, const double *d, double step, double bs_scale, double *x, double *g,
+                       double *s, double *y, const double *const *s_old, const double *const *y_old, int64_t n,
+                       cudaStream_t stream, double *hist, double *gram_out, double *newdot_out) {
+    int grid = 1;
+    if (!o->sequential) {
+        const int64_t tile = (int64_t)kThreads * LB_CG_U, nv = n >> 1;
+        int64_t tiles = (nv + tile - 1) / tile;
+        if (tiles < 1) tiles = 1;
+        if (tiles > (int64_t)o->dev.sm_count * LB_CG_BLOCKS) tiles = (int64_t)o->dev.sm_count * LB_CG_BLOCKS;
+        grid = (int)tiles;
+    }
+    const int threads = o->sequential ? 1 : kThreads;
+    ReduceWs ws = o->ws;
+    ws.partials = o->wide_partials;
+    ws.peer.nranks = 0;
+    if (rosen_streaming(o, n)) {
+        RosenCommitGramOp<true, G> op{xp, d, x, g, s, y, step, bs_scale, {}, {}};
+        for (int k = 0; k < G; ++k) { op.so[k] = s_old[k]; op.yo[k] = y_old[k]; }
+        k_rosenbrock_commit_gram<true, G><<<grid, threads, 0, stream>>>(op, n, ws, hist, gram_out, newdot_out);
+    } else {
+        RosenCommitGramOp<false, G> op{xp, d, x, g, s, y, step, bs_scale, {}, {}};
+        for (int k = 0; k < G; ++k) { op.so[k] = s_old[k]; op.yo[k] = y_old[k]; }
+        k_rosenbrock_commit_gram<false, G><<<grid, threads, 0, stream>>>(op, n, ws, hist, gram_out, newdot_out);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
+int commit_gram_impl(Objective *o, const double *xp, const double *d, double step, double bs_scale, double *x, double *g,
+                     double *s, double *y, const double *const *s_old, const double *const *y_old, int n_old, int64_t n,
+                     cudaStream_t stream, double *hist, double *gram_out, double *newdot_out) {
+    if (o->kind != OBJ_ROSENBROCK || !o->recompute_gp || n_old < 0 || n_old > kCompactGroupMax) return LBFGSB200_ERR_UNSUPPORTED;
+    if (sums_over_ranks(o)) return LBFGSB200_ERR_UNSUPPORTED;   // 5 n_old + 7 sums do not fit one mailbox entry
+    if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (!o->wide_partials &&
+        cudaMalloc((void **)&o->wide_partials, sizeof(double) * (size_t)(5 * kCompactGroupMax + 7) * (size_t)o->ws.stride) != cudaSuccess) {
+        o->wide_partials = nullptr;
+        cudaGetLastError();
+        return LBFGSB200_ERR_UNSUPPORTED;   // the caller runs commit + pass A separately
+    }
+#define LB_CG(G) commit_gram_launch<G>(o, xp, d, step, bs_scale, x, g, s, y, s_old, y_old, n, stream, hist, gram_out, newdot_out)
+    switch (n_old) {
+        case 0: return LB_CG(0);
+        case 1: return LB_CG(1);
+        case 2: return LB_CG(2);
+        case 3: return LB_CG(3);
+        case 4: return LB_CG(4);
+        default: return LB_CG(5);
+    }
+#undef LB_CG
+}
+
 int eval_impl(Objective *o, const double *x, double *g, int64_t n, cudaStream_t stream, double *fx) {
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     switch (o->kind) {
@@ -1105,6 +1232,18 @@ int lbfgsb200_objective_commit(void *objective, const double *xp_dev, const doub
     return lb::commit_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, gp_dev, step, bs_scale, x_dev, g_dev,
                            s_dev, y_dev, n_local, (cudaStream_t)stream, out_dev);
 }
+int lbfgsb200_objective_commit_gram(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev, double step,
+                                    double bs_scale, double *x_dev, double *g_dev, double *s_dev, double *y_dev,
+                                    const double *const *s_old_dev, const double *const *y_old_dev, int n_old, int64_t n_local,
+                                    void *stream, double *out_dev, double *gram_out_dev, double *newdot_out_dev) {
+    (void)gp_dev;   // recomputed from xp
+    if (!objective || !xp_dev || !d_dev || !x_dev || !g_dev || !s_dev || !y_dev || !out_dev || !gram_out_dev || !newdot_out_dev ||
+        (n_old > 0 && (!s_old_dev || !y_old_dev)))
+        return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::commit_gram_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, step, bs_scale, x_dev, g_dev, s_dev,
+                                y_dev, s_old_dev, y_old_dev, n_old, n_local, (cudaStream_t)stream, out_dev, gram_out_dev,
+                                newdot_out_dev);
+}
 int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fused_ops_t *out) {
     lb::Objective *o = reinterpret_cast<lb::Objective *>(objective);
     if (!o || !out) return LBFGSB200_ERR_INVALID_PARAM;
@@ -1112,12 +1251,14 @@ int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fu
     out->trial = nullptr;
     out->probe = nullptr;
     out->commit = nullptr;
+    out->commit_gram = nullptr;
     out->user = o;
     out->flags = 0;
     if (o->kind == lb::OBJ_ROSENBROCK) {
         out->trial = lbfgsb200_objective_trial_eval;
         out->probe = lbfgsb200_objective_probe;
         out->commit = lbfgsb200_objective_commit;
+        if (o->recompute_gp) out->commit_gram = lbfgsb200_objective_commit_gram;
         if (lb::sums_over_ranks(o)) out->flags |= LBFGSB200_FUSED_SUMS_OVER_RANKS;
         if (o->recompute_gp) out->flags |= LBFGSB200_FUSED_COMMIT_SKIPS_GP;
     }
@@ -1130,6 +1271,7 @@ void lbfgsb200_objective_destroy(lbfgsb200_objective_t *objective) {
     if (o->gpart) cudaFree(o->gpart);
     if (o->gfused) cudaFree(o->gfused);
     if (o->xall) cudaFree(o->xall);
+    if (o->wide_partials) cudaFree(o->wide_partials);
     lb::free_reduce_ws(&o->ws);
     delete o;
 }

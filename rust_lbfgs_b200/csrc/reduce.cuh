@@ -147,6 +147,51 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NACC], const ReduceWs 
     }
 }
 
+// The same two levels for a kernel whose sums belong to three different consumers: accumulators [0, n0) go to out0,
+// [n0, n0 + n1) to out1, the rest to out2.  No cross-GPU level (single-GPU fusions only); ws.partials must hold
+// NACC * ws.stride doubles.
+template <int NACC>
+__device__ __forceinline__ void grid_reduce_split(double (&acc)[NACC], const ReduceWs &ws, double *__restrict__ out0, int n0,
+                                                  double *__restrict__ out1, int n1, double *__restrict__ out2) {
+    __shared__ double sm[NACC][kWarps];
+    __shared__ bool is_last;
+    auto put = [&](int a, double v) {
+        if (a < n0) out0[a] = v;
+        else if (a < n0 + n1) out1[a - n0] = v;
+        else out2[a - n0 - n1] = v;
+    };
+    if (blockDim.x == 1) {  // reference-order mode
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) put(a, acc[a]);
+        return;
+    }
+    block_sum<NACC>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) __stcg(&ws.partials[(size_t)a * ws.stride + blockIdx.x], acc[a]);
+        __threadfence();
+        unsigned int t = atomicAdd(ws.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads)
+            v += __ldcg(&ws.partials[(size_t)a * ws.stride + i]);
+        acc[a] = v;
+    }
+    __syncthreads();  // sm reuse
+    block_sum<NACC>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) put(a, acc[a]);
+        *ws.ticket = 0u;
+    }
+}
+
 // 128-bit streaming loads/stores.  kStream marks the instantiations used when the vectors are far larger than L2
 // (n = 1e8: 0.8 GB per vector vs 126 MB of L2); which cache hints they use is a build-time policy (below).
 // Cache hints for the streaming (working set >> L2) instantiations, measured on B200 at n = 1e8

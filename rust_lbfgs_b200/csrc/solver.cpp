@@ -319,6 +319,7 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     graphs_enabled_ = env_int("LBFGSB200_GRAPHS", 1) != 0;
     small_enabled_ = env_int("LBFGSB200_SMALL", 1) != 0;
     speculate_ = env_int("LBFGSB200_SPECULATE", 1) != 0;
+    commit_gram_enabled_ = env_int("LBFGSB200_COMMIT_GRAM", 1) != 0;
     ring_stride_ = vec_bytes / (int64_t)sizeof(double);
     // process-wide default (lbfgsb200_set_default_direction, else LBFGSB200_DIRECTION=compact); lbfgsb200_set_direction wins
     int dflt = g_default_direction.load();
@@ -660,12 +661,47 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
     const double vbytes = 8.0 * (double)n_;
     double *hist = slot(SLOT_HIST);   // {s.s, y.s, y.y, s.(-g | -pg), s.Bs}
     int rc = 0;
+    gram_fused_ = 0;
     if (use_probe()) {
-        prof_begin(LBFGSB200_K_COMMIT);
-        const int erc = fused_.commit(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
-                                      Y_[slot_new], n_, (void *)L.stream, hist);
-        prof_end(LBFGSB200_K_COMMIT, ((fused_.flags & LBFGSB200_FUSED_COMMIT_SKIPS_GP) ? 6.0 : 7.0) * vbytes);
-        launch_counter_ += 1;
+        int erc = LBFGSB200_ERR_UNSUPPORTED;
+        const bool multi = comm_ && comm_size(comm_) > 1;
+        if (compact_ && commit_gram_enabled_ && fused_.commit_gram && !damping && !multi) {
+            // compact direction: the commit also forms the new pair's inner products with the first group of older
+            // ring pairs (pass A for them), from the registers that hold s, y and g — 3 V less than commit + k_gram
+            const int64_t bnd = (m_ < k_ - 1) ? m_ : (k_ - 1);
+            const int nold = (int)bnd - 1;
+            const int groups = nold > 0 ? (nold + kCompactGroupMax - 1) / kCompactGroupMax : 1;
+            const int cnt = nold > 0 ? (nold + groups - 1) / groups : 0;
+            const double *sp[kCompactGroupMax], *yp[kCompactGroupMax];
+            for (int c = 0; c < cnt; ++c) {
+                const int j = (int)((slot_new + m_ - (1 + c)) % m_);
+                sp[c] = S_[j];
+                yp[c] = Y_[j];
+            }
+            prof_begin(LBFGSB200_K_COMMIT);
+            erc = fused_.commit_gram(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
+                                     Y_[slot_new], sp, yp, cnt, n_, (void *)L.stream, hist, cmp_sums_, cmp_sums_ + 5 * nold);
+            if (erc == 0) {
+                prof_end(LBFGSB200_K_COMMIT, (6.0 + 2.0 * cnt) * vbytes);
+                launch_counter_ += 1;
+                gram_fused_ = cnt > 0 ? cnt : -1;   // -1: the newest pair's own two sums only
+            } else {   // not offered for this shape: undo the pending event pair and run the plain commit
+                if (timing_ && ((timing_mask_ >> LBFGSB200_K_COMMIT) & 1u)) {
+                    event_pool_.push_back(pending_.back().a);
+                    event_pool_.push_back(pending_.back().b);
+                    pending_.pop_back();
+                }
+                cudaGetLastError();
+                if (erc == LBFGSB200_ERR_UNSUPPORTED) commit_gram_enabled_ = false;
+            }
+        }
+        if (erc != 0) {
+            prof_begin(LBFGSB200_K_COMMIT);
+            erc = fused_.commit(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
+                                Y_[slot_new], n_, (void *)L.stream, hist);
+            prof_end(LBFGSB200_K_COMMIT, ((fused_.flags & LBFGSB200_FUSED_COMMIT_SKIPS_GP) ? 6.0 : 7.0) * vbytes);
+            launch_counter_ += 1;
+        }
         if (erc != 0) return fail(erc <= LBFGSB200_ERR_CUDA ? erc : LBFGSB200_ERR_EVALUATE, "the objective's commit failed");
         rc = reduce_across_ranks(SLOT_HIST, 5, /*ours=*/fused_exchanges());
     } else {
@@ -738,17 +774,20 @@ int Solver::compact_direction(const Launch &L, int64_t bound, int *so_last) {
     const double *src = owl_ ? pg_ : gbuf_[cur_g_];   // d0 = -g | -pg, core.rs:95-101
     auto slot_of = [&](int t) { return (e + m - t) % m; };   // the t-th newest pair
     if (nold == 0) {
-        prof_begin(LBFGSB200_K_BACKWARD);
-        launch_gram(L, S_[e], Y_[e], src, nullptr, nullptr, 0, true, n_, cmp_partials_, cmp_sums_);
-        prof_end(LBFGSB200_K_BACKWARD, 2.0 * vbytes);
+        if (gram_fused_ == 0) {
+            prof_begin(LBFGSB200_K_BACKWARD);
+            launch_gram(L, S_[e], Y_[e], src, nullptr, nullptr, 0, true, n_, cmp_partials_, cmp_sums_);
+            prof_end(LBFGSB200_K_BACKWARD, 2.0 * vbytes);
+        }
     } else {
         const int groups = (nold + kCompactGroupMax - 1) / kCompactGroupMax;
         const int per = (nold + groups - 1) / groups;
-        for (int t0 = 1; t0 <= nold; t0 += per) {
+        // the objective's commit_gram already produced the first group (and the newest pair's own two sums)
+        for (int t0 = 1 + (gram_fused_ > 0 ? gram_fused_ : 0); t0 <= nold; t0 += per) {
             const int cnt = (nold - t0 + 1 < per) ? (nold - t0 + 1) : per;
             const double *sp[kCompactGroupMax], *yp[kCompactGroupMax];
             for (int c = 0; c < cnt; ++c) { sp[c] = S_[slot_of(t0 + c)]; yp[c] = Y_[slot_of(t0 + c)]; }
-            const bool newdot = t0 + cnt > nold;      // the last group also sums y_new.d0 and y_new.y_new
+            const bool newdot = gram_fused_ == 0 && t0 + cnt > nold;   // the last group also sums y_new.d0 and y_new.y_new
             prof_begin(LBFGSB200_K_BACKWARD);
             launch_gram(L, S_[e], Y_[e], src, sp, yp, cnt, newdot, n_, cmp_partials_, cmp_sums_ + 5 * (t0 - 1));
             prof_end(LBFGSB200_K_BACKWARD, (3.0 + 2.0 * cnt) * vbytes);

@@ -197,6 +197,9 @@ class Solver {
 
     // compact direction: S^T Y, Y^T Y (m x m each), this iteration's sums, the coefficients, wide reduction partials
     bool compact_ = false;
+    bool commit_gram_enabled_ = true;   // LBFGSB200_COMMIT_GRAM=0 disables; cleared when the objective declines
+    int gram_fused_ = 0;                // older ring pairs whose pass-A sums this iteration's commit produced (-1: none, but
+                                        // the newest pair's own two sums)
     double *cmp_block_ = nullptr;
     double *cmp_sy_ = nullptr, *cmp_yy_ = nullptr, *cmp_sums_ = nullptr, *cmp_coefs_ = nullptr, *cmp_partials_ = nullptr;
 

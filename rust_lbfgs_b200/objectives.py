@@ -50,6 +50,7 @@ class _Builtin:
         if mode == "trial":
             ops.probe = None
             ops.commit = None
+            ops.commit_gram = None
         if not (ops.trial or ops.probe):
             return None
         return ops

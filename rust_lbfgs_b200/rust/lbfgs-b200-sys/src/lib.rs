@@ -114,6 +114,13 @@ pub type lbfgsb200_commit_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp
     gp_dev: *const f64, step: f64, bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
     n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
 
+/// The commit fused with pass A of the compact search direction (include/lbfgsb200.h: lbfgsb200_commit_gram_fn).
+pub type lbfgsb200_commit_gram_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
+    gp_dev: *const f64, step: f64, bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
+    s_old_dev: *const *const f64, y_old_dev: *const *const f64, n_old: c_int, n_local: i64, stream: *mut c_void,
+    out_dev: *mut f64, gram_out_dev: *mut f64, newdot_out_dev: *mut f64) -> c_int>;
+
+pub const LBFGSB200_FUSED_OPS_SIZE_V1: i64 = 48;
 pub const LBFGSB200_FUSED_SUMS_OVER_RANKS: i64 = 1;
 pub const LBFGSB200_FUSED_COMMIT_SKIPS_GP: i64 = 2;
 /// `lbfgsb200_fused_ops_t`: what an objective offers beyond evaluate.
@@ -126,10 +133,12 @@ pub struct lbfgsb200_fused_ops_t {
     pub commit: lbfgsb200_commit_fn,
     pub user: *mut c_void,
     pub flags: i64,
+    pub commit_gram: lbfgsb200_commit_gram_fn,
 }
 impl Default for lbfgsb200_fused_ops_t {
     fn default() -> Self {
-        Self { struct_size: std::mem::size_of::<Self>() as i64, trial: None, probe: None, commit: None, user: std::ptr::null_mut(), flags: 0 }
+        Self { struct_size: std::mem::size_of::<Self>() as i64, trial: None, probe: None, commit: None, user: std::ptr::null_mut(), flags: 0,
+               commit_gram: None }
     }
 }
 
@@ -231,6 +240,11 @@ extern "C" {
     pub fn lbfgsb200_objective_commit(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
                                       bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
                                       n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
+    pub fn lbfgsb200_objective_commit_gram(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
+                                           bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
+                                           s_old_dev: *const *const f64, y_old_dev: *const *const f64, n_old: c_int, n_local: i64,
+                                           stream: *mut c_void, out_dev: *mut f64, gram_out_dev: *mut f64,
+                                           newdot_out_dev: *mut f64) -> c_int;
     pub fn lbfgsb200_objective_fused_ops(objective: *mut lbfgsb200_objective_t, out: *mut lbfgsb200_fused_ops_t) -> c_int;
     pub fn lbfgsb200_objective_last_path(objective: *const lbfgsb200_objective_t) -> c_int;
     pub fn lbfgsb200_objective_set_lj_fast(objective: *mut lbfgsb200_objective_t, fast: c_int) -> c_int;

@@ -220,3 +220,21 @@ def test_compact_rejects_large_m_and_late_switch():
         R.lbfgs().with_m(33).with_direction("compact").build(x, R.Rosenbrock())
     with pytest.raises(ValueError):
         R.lbfgs().with_direction("gram")
+
+
+def test_commit_fused_with_pass_a_equals_commit_then_pass_a(monkeypatch):
+    """The Rosenbrock commit fused with pass A (lbfgsb200_commit_gram_fn: the new pair's inner products formed from the
+    registers that hold s, y, g) against commit + k_gram: bit-identical in reference order (every sum is the same
+    sequential fold), equal to rounding with tree sums; m = 6 (one group) and m = 20 (first group fused, three by k_gram)."""
+    for m, n, iters in ((6, 4098, 30), (20, 1000, 40), (1, 100, 10)):
+        x0 = perturbed_x0(n)
+        runs = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("LBFGSB200_COMMIT_GRAM", fused)
+            runs["seq" + fused] = gpu_minimize(seq().with_m(m).with_max_iterations(iters), x0, R.Rosenbrock())
+            runs["tree" + fused] = gpu_minimize(R.lbfgs().with_m(m).with_max_iterations(iters).with_direction("compact"), x0, R.Rosenbrock())
+        monkeypatch.delenv("LBFGSB200_COMMIT_GRAM")
+        assert_bit_identical(runs["seq0"], runs["seq1"], f"m={m}")
+        a, b = runs["tree0"], runs["tree1"]
+        assert [t["ncall"] for t in a["trace"]] == [t["ncall"] for t in b["trace"]] and len(a["trace"]) == iters
+        assert np.max(np.abs(a["x"] - b["x"])) <= 1e-9 * np.max(np.abs(a["x"]))
