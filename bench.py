@@ -540,6 +540,24 @@ def run_ours(args):
         "note": "one lbfgsb200_minimize_host_ex() call on a pinned HOST buffer: H2D of x0, solver creation, build, "
                 "W+K iterations, D2H of x, teardown",
     }
+    # the same call with the opt-in compact search direction (reported inside the `compact_direction` block)
+    e2e_compact = None
+    if not args.no_compact and m <= 32:
+        try:
+            xh[0::2] = -1.2
+            xh[1::2] = 1.0
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            repc = builder.with_direction("compact").minimize_host(xh, obj, None, device=local_rank)
+            t1 = time.perf_counter()
+            barrier()
+            sc = D.max_over_ranks(t1 - t0)
+            e2e_compact = {"value": ((repc.niter - 1) / sc) * n_global / N_REF, "unit": UNIT, "iterations": repc.niter - 1,
+                           "seconds": sc, "evaluations": repc.neval,
+                           "note": "one lbfgsb200_minimize_host_ex() call on the pinned host buffer, as `e2e` above"}
+        except Exception as e:
+            e2e_compact = {"error": repr(e)}
     # what the two bulk copies of that call cost on their own, all ranks copying at the same time (the limiter of
     # e2e on N GPUs of one host: they share the host's memory and PCIe root complexes)
     xd = torch.empty(n_local, dtype=torch.float64, device=dev)
@@ -580,6 +598,7 @@ def run_ours(args):
                                     not args.no_cpu_baseline, N_REF, UNIT)
         except Exception as e:   # never break the headline measurement
             compact = {"error": repr(e)}
+        compact["e2e"] = e2e_compact
 
     # ---- BASELINE configs[4]: Rosenbrock n = 2^31, m = 20 sharded over 8 GPUs = 2^28 elements per GPU -----------
     # Run at every N (weak scaling at 2^28 per GPU), so the driver's own N = 1, 2, 4, 8 set yields north_star's

@@ -83,6 +83,12 @@ cudaError_t launch_two_loop_small(const Launch &L, int device, int64_t n, int m,
                                   bool constrain, double *step_out);
 
 
+// the compact direction (below) for n <= two_loop_small_max_n(): pass A + scalar recursions + pass B in ONE cluster launch
+cudaError_t launch_compact_small(const Launch &L, int device, int64_t n, int m, int bound, int slot_new, double *d,
+                                 const double *dsrc, const double *ring, int64_t stride, double *ys_dev, double *SY, double *YY,
+                                 const double *hist, double *out, bool owl, int64_t start, int64_t end, int64_t goff,
+                                 double max_step, bool constrain, double *step_out);
+
 // The opt-in compact search direction (compact.cu; src/lbfgs.rs:569-604 with the 2 * bound scalars derived from inner
 // products of the unmodified ring vectors): pass A for the t-th newest slots given by s[] / y[] (cnt <=
 // kCompactGroupMax older slots per launch, 5 sums each; `newdot` adds {y_new.d0, y_new.y_new}), the scalar recursions,

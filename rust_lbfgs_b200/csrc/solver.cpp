@@ -665,7 +665,7 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
     if (use_probe()) {
         int erc = LBFGSB200_ERR_UNSUPPORTED;
         const bool multi = comm_ && comm_size(comm_) > 1;
-        if (compact_ && commit_gram_enabled_ && fused_.commit_gram && !damping && !multi) {
+        if (compact_ && commit_gram_enabled_ && fused_.commit_gram && !damping && !multi && !small_eligible()) {
             // compact direction: the commit also forms the new pair's inner products with the first group of older
             // ring pairs (pass A for them), from the registers that hold s, y and g — 3 V less than commit + k_gram
             const int64_t bnd = (m_ < k_ - 1) ? m_ : (k_ - 1);
@@ -805,6 +805,29 @@ int Solver::compact_direction(const Launch &L, int64_t bound, int *so_last) {
     prof_end(LBFGSB200_K_FORWARD, (2.0 * b + 2.0) * vbytes);
     const int rc = reduce_across_ranks(SLOT_LOOP_A, 3);
     if (rc != 0) return fail(rc, "ncclAllReduce failed");
+    *so_last = SLOT_LOOP_A;
+    return 0;
+}
+
+// The compact direction in the launch-bound regime: pass A + scalar recursions + pass B in ONE cluster launch (small.cu).
+int Solver::compact_small(const Launch &L, int64_t bound, int *so_last) {
+    const double vbytes = 8.0 * (double)n_;
+    prof_begin(LBFGSB200_K_UPDATE_SMALL);
+    const cudaError_t e = launch_compact_small(L, dev_.device, n_, (int)m_, (int)bound, (int)end_, d_, owl_ ? pg_ : gbuf_[cur_g_],
+                                               S_[0], ring_stride_, ys_dev_, cmp_sy_, cmp_yy_, slot(SLOT_HIST), slot(SLOT_LOOP_A),
+                                               owl_, owl_start_, owl_end_, goff_, p_.max_step_size,
+                                               p_.constrain_step_size != 0, slot(SLOT_STEP));
+    if (e != cudaSuccess) {   // refused (cluster shape): never try again, use the three-launch form
+        cudaGetLastError();
+        if (timing_ && ((timing_mask_ >> LBFGSB200_K_UPDATE_SMALL) & 1u)) {
+            event_pool_.push_back(pending_.back().a);
+            event_pool_.push_back(pending_.back().b);
+            pending_.pop_back();
+        }
+        small_enabled_ = false;
+        return compact_direction(L, bound, so_last);
+    }
+    prof_end(LBFGSB200_K_UPDATE_SMALL, (4.0 * (double)bound + 2.0) * vbytes);
     *so_last = SLOT_LOOP_A;
     return 0;
 }
@@ -993,7 +1016,8 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     rc = enqueue_history(L, xp, gp, stp_eval);
     if (rc != 0) return rc;
     bool small_ran = false;
-    if (compact_) rc = compact_direction(L, bound, &so_last);
+    if (compact_ && small_eligible()) { rc = compact_small(L, bound, &so_last); small_ran = small_enabled_; }
+    else if (compact_) rc = compact_direction(L, bound, &so_last);
     else if (small_eligible()) { rc = two_loop_small(L, bound, &so_last); small_ran = small_enabled_; }
     else if (graph_eligible(bound)) rc = two_loop_graphed(L, gp, bound, &so_last);
     else rc = enqueue_two_loop(L, gp, bound, &so_last);

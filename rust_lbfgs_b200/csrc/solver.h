@@ -121,6 +121,7 @@ class Solver {
     int enqueue_two_loop(const Launch &L, const double *gp, int64_t bound, int *so_last);
     // the compact direction (compact.cu): pass A + scalar recursions + pass B instead of the 2 * bound trips
     int compact_direction(const Launch &L, int64_t bound, int *so_last);
+    int compact_small(const Launch &L, int64_t bound, int *so_last);   // the same in one cluster launch (n <= 2^18)
     bool small_eligible() const;   // the cluster-persistent two-loop kernel (small.cu) applies
     int two_loop_small(const Launch &L, int64_t bound, int *so_last);
     bool graph_eligible(int64_t bound) const;

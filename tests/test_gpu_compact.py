@@ -238,3 +238,38 @@ def test_commit_fused_with_pass_a_equals_commit_then_pass_a(monkeypatch):
         a, b = runs["tree0"], runs["tree1"]
         assert [t["ncall"] for t in a["trace"]] == [t["ncall"] for t in b["trace"]] and len(a["trace"]) == iters
         assert np.max(np.abs(a["x"] - b["x"])) <= 1e-9 * np.max(np.abs(a["x"]))
+
+
+@pytest.mark.parametrize("n", [2, 100, 2050, 10_001, 65_536, 131_074, 262_144])
+def test_compact_small_cluster_kernel_matches_the_three_launch_form(n, monkeypatch):
+    """k_compact_small (small.cu: pass A + scalar recursions + pass B in ONE thread-block-cluster launch, two cluster-wide
+    reductions per iteration) against k_gram + k_compact_solve + k_direction: same element-wise arithmetic and the same
+    scalar recursions, a different summation tree — identical evaluation counts, x to 1e-11 over 30 iterations."""
+    def run(small, builder, x0, evaluate):
+        monkeypatch.setenv("LBFGSB200_SMALL", "1" if small else "0")
+        return gpu_minimize(builder().with_direction("compact"), x0, evaluate, record_x=True)
+    even = n - (n % 2)
+    cases = [("defaults", lambda: R.lbfgs().with_max_iterations(30), perturbed_x0(even), R.Rosenbrock()),
+             ("m=1", lambda: R.lbfgs().with_m(1).with_max_iterations(20), perturbed_x0(even), R.Rosenbrock()),
+             ("m=20 damping", lambda: R.lbfgs().with_m(20).with_damping(True).with_linesearch_algorithm("BacktrackingStrongWolfe")
+              .with_max_iterations(30), perturbed_x0(even), R.Rosenbrock())]
+    if n >= 100:
+        cases.append(("owl-qn sub-range", lambda: R.lbfgs().with_orthantwise(0.5, 3, even - 5).with_max_iterations(30),
+                      perturbed_x0(even), R.Rosenbrock()))
+    if n % 2:   # odd length: a user evaluate (quadratic) — the Rosenbrock objective needs pairs
+        import torch
+        w = torch.linspace(0.5, 2.0, n, dtype=torch.float64, device="cuda:0")
+
+        def quad(x, gx):
+            gx.copy_(w * (x - 1.0))
+            return 0.5 * torch.sum(w * (x - 1.0) ** 2)
+        cases = [("odd n, user evaluate", lambda: R.lbfgs().with_max_iterations(15), np.linspace(-1.0, 2.0, n), quad)]
+    for name, builder, x0, evaluate in cases:
+        a = run(True, builder, x0, evaluate)
+        b = run(False, builder, x0, evaluate)
+        assert a["status_name"] == b["status_name"], (name, a["status_name"], b["status_name"], a["error"], b["error"])
+        assert len(a["trace"]) == len(b["trace"]) > 2, name
+        for s, t in zip(a["trace"], b["trace"]):
+            assert s["ncall"] == t["ncall"], (name, s["niter"])
+            assert np.max(np.abs(s["x"] - t["x"])) <= 1e-11 * max(1.0, np.max(np.abs(t["x"]))), (name, s["niter"])
+    monkeypatch.delenv("LBFGSB200_SMALL")
