@@ -2,6 +2,7 @@
 
     python examples/sample.py            # device-resident: x is a CUDA tensor, the built-in device objective
     python examples/sample.py --host     # the reference's exact shape: x is a HOST slice, evaluate a HOST closure
+    python examples/sample.py --compact  # device-resident, with the opt-in compact search direction
 """
 import os
 import sys
@@ -42,7 +43,8 @@ def main():
     else:
         import torch
         xd = torch.tensor(x, device="cuda:0")
-        prb = R.lbfgs().minimize(xd, R.Rosenbrock(), progress)
+        builder = R.lbfgs().with_direction("compact") if "--compact" in sys.argv else R.lbfgs()
+        prb = builder.minimize(xd, R.Rosenbrock(), progress)
         x0, x1 = float(xd[0]), float(xd[1])
     print(f"  fx = {prb.fx}, x[0] = {x0}, x[1] = {x1}\n")
     return prb
