@@ -432,13 +432,15 @@ void gram_group(const Launch &L, bool newdot, const double *sn, const double *yn
                 const double *const *y, int64_t n, const ReduceWs &ws, double *out) {
     GramPtrs<G> p{};
     for (int k = 0; k < G; ++k) { p.s[k] = s[k]; p.y[k] = y[k]; }
-    constexpr bool kNoOld = G == 0;   // the newest pair alone: always with its own two sums
-    if (L.streaming) {
-        if (newdot || kNoOld) gram_launch<true, G, true>(L, sn, yn, src, p, n, ws, out);
-        else gram_launch<true, G, !kNoOld ? false : true>(L, sn, yn, src, p, n, ws, out);
+    if constexpr (G == 0) {   // the newest pair alone: always with its own two sums
+        if (L.streaming) gram_launch<true, 0, true>(L, sn, yn, src, p, n, ws, out);
+        else gram_launch<false, 0, true>(L, sn, yn, src, p, n, ws, out);
+    } else if (L.streaming) {
+        if (newdot) gram_launch<true, G, true>(L, sn, yn, src, p, n, ws, out);
+        else gram_launch<true, G, false>(L, sn, yn, src, p, n, ws, out);
     } else {
-        if (newdot || kNoOld) gram_launch<false, G, true>(L, sn, yn, src, p, n, ws, out);
-        else gram_launch<false, G, !kNoOld ? false : true>(L, sn, yn, src, p, n, ws, out);
+        if (newdot) gram_launch<false, G, true>(L, sn, yn, src, p, n, ws, out);
+        else gram_launch<false, G, false>(L, sn, yn, src, p, n, ws, out);
     }
 }
 
