@@ -95,7 +95,10 @@ struct GramOp {
         elem(G > 0 ? sn[e] : 0.0, yn[e], src[e], sk, yk, acc);
     }
 };
-template <int G> struct GramU { static constexpr int value = G == 0 ? 8 : (G == 1 ? 4 : (G == 2 ? 3 : 2)); };
+#ifndef LB_GRAM_U
+#define LB_GRAM_U 2   // pairs per thread per tile of pass A with 3 .. 5 older ring pairs per launch (tuned: profiles/r02_tuning.md)
+#endif
+template <int G> struct GramU { static constexpr int value = G == 0 ? 8 : (G == 1 ? 4 : (G == 2 ? 3 : LB_GRAM_U)); };
 
 template <bool S, int G, bool NEWDOT>
 __global__ void __launch_bounds__(kThreads, 1) k_gram(GramOp<S, G, NEWDOT> op, int64_t n, ReduceWs ws, double *out) {

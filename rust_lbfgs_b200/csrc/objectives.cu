@@ -249,7 +249,7 @@ struct RosenCommitGramOp {
     __device__ __forceinline__ void tail(int64_t, double (&)[kAcc]) const {}
 };
 #ifndef LB_CG_U
-#define LB_CG_U 2        // pairs per thread per tile ...
+#define LB_CG_U 3        // pairs per thread per tile ...
 #endif
 #ifndef LB_CG_BLOCKS
 #define LB_CG_BLOCKS 1   // ... and resident CTAs per SM of the fused commit + pass A kernel (tuned: profiles/r02_tuning.md)

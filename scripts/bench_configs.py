@@ -51,6 +51,8 @@ def solve(builder, x, obj, tag, extra=None, max_iter=None):
                evaluations=rep.neval, fx=rep.fx, gnorm=rep.gnorm,
                it_per_s=(len(ncalls) - 1) / (t1 - t0), ms_per_evaluation=1e3 * (t1 - t0) / max(1, rep.neval))
     rec.update(extra or {})
+    if "objective_ms_alone" in rec and rec["iterations"] > 0:   # what the solver adds around the objective, per iteration
+        rec["solver_ms_per_iteration"] = (1e3 * (t1 - t0) - rec["evaluations"] * rec["objective_ms_alone"]) / rec["iterations"]
     rec["n_gpus"] = WORLD
     if RANK == 0:
         print(json.dumps(rec), flush=True)
@@ -119,13 +121,14 @@ def cfg3(full):
         L.lbfgsb200_objective_eval(obj._user_ptr(LOCAL), w.data_ptr(), gx.data_ptr(), ncol, st, fx.data_ptr())
     t1 = sync_time()
     xbytes = 8.0 * nrow * ncol
+    glm_ms = 1e3 * (t1 - t0) / reps
     if RANK == 0:
         print(json.dumps(dict(config=f"cfg3 glm objective alone {nrow_all}x{ncol} over {WORLD} GPU(s)",
                               ms_per_evaluation=1e3 * (t1 - t0) / reps, X_GB_per_gpu=xbytes / 1e9,
                               GBps_per_gpu_one_pass_equivalent=xbytes / 1e9 / ((t1 - t0) / reps))), flush=True)
     c = 1.0 * nrow_all / 500.0   # tests/owlqn.rs uses c = 1 with 500 rows
     solve(R.lbfgs().with_orthantwise(c, 1).with_epsilon(1e-4), w, obj, f"cfg3 owlqn logistic {nrow_all}x{ncol} c={c}",
-          extra=dict(X_GB_per_gpu=xbytes / 1e9), max_iter=60)
+          extra=dict(X_GB_per_gpu=xbytes / 1e9, objective_ms_alone=glm_ms), max_iter=60)
     if RANK == 0:
         print(json.dumps(dict(config="cfg3 sparsity", nonzeros=int((w != 0).sum()), ncol=ncol)), flush=True)
 
@@ -152,6 +155,7 @@ def cfg4(full):
     L = R.lib()
     st = int(torch.cuda.current_stream().cuda_stream)
     gx, fx = torch.empty_like(x0), torch.zeros(1, dtype=torch.float64, device=DEV)
+    lj_ms = {}
     for fast in (False, True):
         lj = R.LennardJones(fast=fast)
         if COMM is not None:
@@ -164,6 +168,7 @@ def cfg4(full):
         for _ in range(reps):
             L.lbfgsb200_objective_eval(h, x0.data_ptr(), gx.data_ptr(), x0.numel(), st, fx.data_ptr())
         t1 = sync_time()
+        lj_ms[fast] = 1e3 * (t1 - t0) / reps
         if RANK == 0:
             ms = 1e3 * (t1 - t0) / reps
             print(json.dumps(dict(config=f"cfg4 lj objective alone, {na} atoms over {WORLD} GPU(s)",
@@ -180,7 +185,8 @@ def cfg4(full):
                 b = b.with_shard(COMM, flat.size, offs[RANK])
             x = x0.clone()
             solve(b, x, lj, f"cfg4 lj {na} atoms {tag}" + (" [fast arithmetic]" if fast else ""),
-                  extra=dict(pairs=na * (na - 1) // 2, parity="UNPINNED"), max_iter=21 if full else 41)
+                  extra=dict(pairs=na * (na - 1) // 2, parity="UNPINNED", objective_ms_alone=lj_ms[fast]),
+                  max_iter=21 if full else 41)
             lj.close()
 
 
