@@ -164,8 +164,9 @@ typedef int (*lbfgsb200_commit_fn)(void *user, const double *xp_dev, const doubl
  * commit does, plus — from the registers that hold the new pair s = x - xp, y = g - gp and the new gradient g — the
  * inner products with n_old <= 5 older ring pairs (HOST arrays of device pointers s_old_dev[k], y_old_dev[k]):
  *   gram_out_dev[5 k + 0..4] = { s_k.d0, y_k.d0, s.y_k, s_k.y, y.y_k },  newdot_out_dev[0..1] = { y.d0, y.y },  d0 = -g
- * (partials of this rank; never combined with LBFGSB200_FUSED_SUMS_OVER_RANKS — return LBFGSB200_ERR_UNSUPPORTED and
- * the solver runs commit + pass A separately, as it does on N > 1 GPUs, with Powell damping and for OWL-QN). */
+ * (ALWAYS partials of this rank, also in out_dev and also when the other entries carry LBFGSB200_FUSED_SUMS_OVER_RANKS:
+ * the solver sums them over the ranks with one all-reduce.  LBFGSB200_ERR_UNSUPPORTED makes the solver run commit +
+ * pass A separately, as it does with Powell damping, which rewrites y after the commit, and for OWL-QN). */
 typedef int (*lbfgsb200_commit_gram_fn)(void *user, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                         double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                         double *y_dev, const double *const *s_old_dev, const double *const *y_old_dev,

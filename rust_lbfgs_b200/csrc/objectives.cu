@@ -1019,7 +1019,7 @@ int commit_gram_impl(Objective *o, const double *xp, const double *d, double ste
                      double *s, double *y, const double *const *s_old, const double *const *y_old, int n_old, int64_t n,
                      cudaStream_t stream, double *hist, double *gram_out, double *newdot_out) {
     if (o->kind != OBJ_ROSENBROCK || !o->recompute_gp || n_old < 0 || n_old > kCompactGroupMax) return LBFGSB200_ERR_UNSUPPORTED;
-    if (sums_over_ranks(o)) return LBFGSB200_ERR_UNSUPPORTED;   // 5 n_old + 7 sums do not fit one mailbox entry
+    // always rank-local partials (5 n_old + 7 sums do not fit one mailbox entry): the solver sums them over the ranks
     if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     if (!o->wide_partials &&

@@ -351,14 +351,14 @@ int Solver::set_direction(int mode) {
         const size_t nsums = (size_t)round_up(5 * m_ + 8, 32);
         const size_t ncoef = (size_t)round_up(1 + 2 * kCompactMaxM, 32);
         const size_t npart = (size_t)(5 * kCompactGroupMax + 2) * (size_t)ws_.stride;
-        const size_t total = 2 * mm + nsums + ncoef + npart;
+        const size_t total = 2 * mm + 32 + nsums + ncoef + npart;
         e = cudaMalloc((void **)&cmp_block_, total * sizeof(double));
         if (e != cudaSuccess) { cmp_block_ = nullptr; return cuda_fail(e, "cudaMalloc(compact direction state)"); }
         e = cudaMemsetAsync(cmp_block_, 0, total * sizeof(double), stream_);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(compact direction state)");
         cmp_sy_ = cmp_block_;
         cmp_yy_ = cmp_sy_ + mm;
-        cmp_sums_ = cmp_yy_ + mm;
+        cmp_sums_ = cmp_yy_ + mm + 32;   // the 32 doubles in front: the commit's history sums ride along with the all-reduce
         cmp_coefs_ = cmp_sums_ + nsums;
         cmp_partials_ = cmp_coefs_ + ncoef;
     }
@@ -665,7 +665,8 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
     if (use_probe()) {
         int erc = LBFGSB200_ERR_UNSUPPORTED;
         const bool multi = comm_ && comm_size(comm_) > 1;
-        if (compact_ && commit_gram_enabled_ && fused_.commit_gram && !damping && !multi && !small_eligible()) {
+        bool hist_done = false;   // the history sums are already summed over the ranks
+        if (compact_ && commit_gram_enabled_ && fused_.commit_gram && !damping && !small_eligible()) {
             // compact direction: the commit also forms the new pair's inner products with the first group of older
             // ring pairs (pass A for them), from the registers that hold s, y and g — 3 V less than commit + k_gram
             const int64_t bnd = (m_ < k_ - 1) ? m_ : (k_ - 1);
@@ -678,13 +679,26 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
                 sp[c] = S_[j];
                 yp[c] = Y_[j];
             }
+            // N > 1 GPUs: commit_gram leaves rank-local partials; its history sums go to the eight doubles in front of
+            // cmp_sums_, so ONE all-reduce covers them and the first group (and the newest pair's two sums when that
+            // is all there is), then they are copied to the history slot
+            double *hist_out = multi ? cmp_sums_ - kMaxAcc : hist;
             prof_begin(LBFGSB200_K_COMMIT);
             erc = fused_.commit_gram(fused_.user, xp, d_, gp, step_eval, -step_, xbuf_[cur_x_], gbuf_[cur_g_], S_[slot_new],
-                                     Y_[slot_new], sp, yp, cnt, n_, (void *)L.stream, hist, cmp_sums_, cmp_sums_ + 5 * nold);
+                                     Y_[slot_new], sp, yp, cnt, n_, (void *)L.stream, hist_out, cmp_sums_, cmp_sums_ + 5 * nold);
             if (erc == 0) {
                 prof_end(LBFGSB200_K_COMMIT, (6.0 + 2.0 * cnt) * vbytes);
                 launch_counter_ += 1;
                 gram_fused_ = cnt > 0 ? cnt : -1;   // -1: the newest pair's own two sums only
+                if (multi) {
+                    prof_.allreduces += 1;
+                    const int count = kMaxAcc + 5 * cnt + (cnt == nold ? 2 : 0);
+                    rc = comm_allreduce_sum(comm_, hist_out, count, stream_);
+                    if (rc != 0) return fail(rc, "ncclAllReduce failed");
+                    const cudaError_t ce = cudaMemcpyAsync(hist, hist_out, 5 * sizeof(double), cudaMemcpyDeviceToDevice, stream_);
+                    if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(history sums)");
+                    hist_done = true;
+                }
             } else {   // not offered for this shape: undo the pending event pair and run the plain commit
                 if (timing_ && ((timing_mask_ >> LBFGSB200_K_COMMIT) & 1u)) {
                     event_pool_.push_back(pending_.back().a);
@@ -703,7 +717,7 @@ int Solver::enqueue_history(const Launch &L, const double *xp, const double *gp,
             launch_counter_ += 1;
         }
         if (erc != 0) return fail(erc <= LBFGSB200_ERR_CUDA ? erc : LBFGSB200_ERR_EVALUATE, "the objective's commit failed");
-        rc = reduce_across_ranks(SLOT_HIST, 5, /*ours=*/fused_exchanges());
+        if (!hist_done) rc = reduce_across_ranks(SLOT_HIST, 5, /*ours=*/fused_exchanges());
     } else {
         prof_begin(LBFGSB200_K_HISTORY);
         launch_history(L, xbuf_[cur_x_], xp, gbuf_[cur_g_], gp, owl_ ? pg_ : nullptr, S_[slot_new], Y_[slot_new], n_, -step_,
@@ -794,9 +808,15 @@ int Solver::compact_direction(const Launch &L, int64_t bound, int *so_last) {
         }
     }
     if (comm_ && comm_size(comm_) > 1) {   // one all-reduce for every sum of the iteration (same bits on every rank)
-        prof_.allreduces += 1;
-        const int rc = comm_allreduce_sum(comm_, cmp_sums_, 5 * nold + 2, stream_);
-        if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        // (what the commit produced: the first group, and the newest pair's two sums when there was no other group,
+        // was summed right behind it)
+        const int done = gram_fused_ > 0 ? gram_fused_ : 0;
+        const int count = (gram_fused_ != 0 && done == nold) ? 0 : 5 * (nold - done) + 2;
+        if (count > 0) {
+            prof_.allreduces += 1;
+            const int rc = comm_allreduce_sum(comm_, cmp_sums_ + 5 * done, count, stream_);
+            if (rc != 0) return fail(rc, "ncclAllReduce failed");
+        }
     }
     launch_compact_solve(L, m, b, e, cmp_sums_, slot(SLOT_HIST), cmp_sy_, cmp_yy_, ys_dev_, cmp_coefs_);
     prof_begin(LBFGSB200_K_FORWARD);
