@@ -173,6 +173,14 @@ typedef int (*lbfgsb200_commit_gram_fn)(void *user, const double *xp_dev, const 
                                         int n_old, int64_t n_local, void *stream, double *out_dev, double *gram_out_dev,
                                         double *newdot_out_dev);
 
+/* Optional: k <= 4 write-free trials in ONE pass over xp and d.  steps[0 .. k) are host values; with step0_dev != NULL
+ * they are instead the More-Thuente extrapolation chain s_0 = *step0_dev, s_{j+1} = s_j + 4 (s_j - s_{j-1}), s_{-1} = 0
+ * (src/line.rs:266), formed on the device with exactly that expression.  out_dev[4 j + 0..3] = { f, g.d, g.g, x.x } at
+ * xp + s_j d, each with the bits lbfgsb200_probe_fn would give for that step; out_dev[4 k + j] = s_j.  The solver asks
+ * for the steps it EXPECTS the search to take and uses a result only if the search then asks for exactly that step. */
+typedef int (*lbfgsb200_probe_multi_fn)(void *user, const double *xp_dev, const double *d_dev, const double *steps,
+                                        const double *step0_dev, int k, int64_t n_local, void *stream, double *out_dev);
+
 /* What an objective offers beyond lbfgsb200_eval_fn.  Unused entries are NULL.  probe needs commit. */
 #define LBFGSB200_FUSED_SUMS_OVER_RANKS 1  /* the callbacks leave sums over ALL ranks in out_dev (the built-in
                                               objectives do, in their kernels' epilogue, once
@@ -188,8 +196,10 @@ typedef struct lbfgsb200_fused_ops {
     int64_t flags;                      /* LBFGSB200_FUSED_* */
     lbfgsb200_commit_gram_fn commit_gram;  /* commit + pass A of the compact direction (struct_size tells whether the
                                               caller's struct has this field: LBFGSB200_FUSED_OPS_SIZE_V1 = without) */
+    lbfgsb200_probe_multi_fn probe_multi;  /* several trials per pass (LBFGSB200_FUSED_OPS_SIZE_V2 = without) */
 } lbfgsb200_fused_ops_t;
 #define LBFGSB200_FUSED_OPS_SIZE_V1 48
+#define LBFGSB200_FUSED_OPS_SIZE_V2 56
 
 /* Progress  src/core.rs:221-250; x/gx are device pointers to this rank's shard */
 typedef struct lbfgsb200_progress {
@@ -459,6 +469,9 @@ int  lbfgsb200_objective_probe(void *objective, const double *xp_dev, const doub
 int  lbfgsb200_objective_commit(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                 double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
                                 double *y_dev, int64_t n_local, void *stream, double *out_dev);
+/* the lbfgsb200_probe_multi_fn of the built-in objectives (Rosenbrock; LBFGSB200_ERR_UNSUPPORTED otherwise) */
+int  lbfgsb200_objective_probe_multi(void *objective, const double *xp_dev, const double *d_dev, const double *steps,
+                                     const double *step0_dev, int k, int64_t n_local, void *stream, double *out_dev);
 /* the lbfgsb200_commit_gram_fn of the built-in objectives (Rosenbrock on one GPU; LBFGSB200_ERR_UNSUPPORTED otherwise) */
 int  lbfgsb200_objective_commit_gram(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev,
                                      double step, double bs_scale, double *x_dev, double *g_dev, double *s_dev,
@@ -474,6 +487,11 @@ lbfgsb200_linesearch_t *lbfgsb200_linesearch_begin(const lbfgsb200_param_t *para
                                                    double finit, double dginit, double step);
 /* returns 1 and *step_out = next trial step; 0 when finished (see _result) */
 int  lbfgsb200_linesearch_next(lbfgsb200_linesearch_t *ls, double *step_out);
+/* between _next and _feed: the steps the search will ask for next IF the pending trial and each one after it
+ * extrapolates (More-Thuente, interval not bracketed: stp + 4 (stp - stx), src/line.rs:266); returns how many were
+ * written (0: not predictable).  Does not change the state: the driver evaluates them ahead of time in the same pass
+ * (lbfgsb200_probe_multi_fn) and uses a result only when the search then asks for exactly that step. */
+int  lbfgsb200_linesearch_predict(const lbfgsb200_linesearch_t *ls, double *steps_out, int kmax);
 void lbfgsb200_linesearch_feed(lbfgsb200_linesearch_t *ls, int eval_ok, double f, double dg);
 /* after _next returned 0: *ncall, final *step; returns LBFGSB200_LS_ERR_* (0 = success) */
 int  lbfgsb200_linesearch_result(lbfgsb200_linesearch_t *ls, int64_t *ncall, double *step);

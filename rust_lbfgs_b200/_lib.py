@@ -80,7 +80,7 @@ COMMIT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
 class FusedOps(C.Structure):
     """lbfgsb200_fused_ops_t: what an objective offers beyond evaluate (function pointers as void*)."""
     _fields_ = [("struct_size", C.c_int64), ("trial", C.c_void_p), ("probe", C.c_void_p), ("commit", C.c_void_p),
-                ("user", C.c_void_p), ("flags", C.c_int64), ("commit_gram", C.c_void_p)]
+                ("user", C.c_void_p), ("flags", C.c_int64), ("commit_gram", C.c_void_p), ("probe_multi", C.c_void_p)]
 
 _lib = None
 
@@ -179,6 +179,7 @@ def lib():
     _sig(L, "lbfgsb200_objective_eval", i32, [vp, vp, vp, i64, vp, vp])
     _sig(L, "lbfgsb200_linesearch_begin", vp, [pp(Param), i32, dbl, dbl, dbl])
     _sig(L, "lbfgsb200_linesearch_next", i32, [vp, pp(dbl)])
+    _sig(L, "lbfgsb200_linesearch_predict", i32, [vp, pp(dbl), i32])
     _sig(L, "lbfgsb200_linesearch_feed", None, [vp, i32, dbl, dbl])
     _sig(L, "lbfgsb200_linesearch_result", i32, [vp, pp(i64), pp(dbl)])
     _sig(L, "lbfgsb200_linesearch_end", None, [vp])

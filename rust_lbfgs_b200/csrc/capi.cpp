@@ -137,7 +137,8 @@ int lbfgsb200_set_fused_ops(lbfgsb200_solver_t *solver, const lbfgsb200_fused_op
     if (!solver) return LBFGSB200_ERR_INVALID_PARAM;
     if (!ops) { S(solver)->set_fused_ops(nullptr); return 0; }
     // a caller built against the header before `commit_gram` was appended passes the shorter struct
-    if ((ops->struct_size != (int64_t)sizeof(lbfgsb200_fused_ops_t) && ops->struct_size != LBFGSB200_FUSED_OPS_SIZE_V1) ||
+    if ((ops->struct_size != (int64_t)sizeof(lbfgsb200_fused_ops_t) && ops->struct_size != LBFGSB200_FUSED_OPS_SIZE_V1 &&
+         ops->struct_size != LBFGSB200_FUSED_OPS_SIZE_V2) ||
         (ops->probe && !ops->commit))
         return LBFGSB200_ERR_INVALID_PARAM;
     lbfgsb200_fused_ops_t full{};
@@ -447,6 +448,10 @@ lbfgsb200_linesearch_t *lbfgsb200_linesearch_begin(const lbfgsb200_param_t *p, i
 }
 int lbfgsb200_linesearch_next(lbfgsb200_linesearch_t *ls, double *step_out) {
     return reinterpret_cast<lb::LineSearchMachine *>(ls)->next_trial(step_out) ? 1 : 0;
+}
+int lbfgsb200_linesearch_predict(const lbfgsb200_linesearch_t *ls, double *steps_out, int kmax) {
+    if (!ls || !steps_out || kmax < 1) return 0;
+    return reinterpret_cast<const lb::LineSearchMachine *>(ls)->predict(steps_out, kmax);
 }
 void lbfgsb200_linesearch_feed(lbfgsb200_linesearch_t *ls, int eval_ok, double f, double dg) {
     reinterpret_cast<lb::LineSearchMachine *>(ls)->feed(eval_ok != 0, f, dg);

@@ -174,6 +174,22 @@ bool LineSearchMachine::next_trial(double *step_out) {
     return true;
 }
 
+int LineSearchMachine::predict(double *steps, int kmax) const {
+    if (done_ || !awaiting_ || !mt_ || brackt_) return 0;
+    double stx = stx_, stp = stp_;
+    int n = 0;
+    int64_t count = count_;
+    while (n < kmax && count + 1 < cfg_.max_linesearch) {
+        const double next = stp + 4.0 * (stp - stx);        // stmax of the NEXT round, :266; the clamp of :583-588 lands on it
+        if (!(next < cfg_.max_step) || !(next > stp)) break;
+        steps[n++] = next;
+        stx = stp;
+        stp = next;
+        ++count;
+    }
+    return n;
+}
+
 void LineSearchMachine::feed(bool eval_ok, double f, double dg) {
     if (done_ || !awaiting_) return;
     awaiting_ = false;

@@ -34,6 +34,12 @@ class LineSearchMachine {
     // (f, dg) at the trial point; eval_ok == false is an Err from evaluate (src/line.rs:286,743).
     void feed(bool eval_ok, double f, double dg);
 
+    // The steps the search WILL ask for next if the trial just handed out (and each one after it) extrapolates — More-
+    // Thuente with the interval not yet bracketed clamps the new trial to stmax = stp + 4 (stp - stx), src/line.rs:266 —
+    // computed with the search's own expression, so a driver may evaluate them ahead of time and compare bit for bit.
+    // Returns how many were written (0: not predictable).  Pure: does not change the state.
+    int predict(double *steps, int kmax) const;
+
     int error() const { return err_; }          // LBFGSB200_LS_ERR_*; non-zero => caller reverts
     int64_t ncall() const { return ncall_; }    // the Ok(count) of the reference
     double step() const { return stp_; }        // the in/out `stp`

@@ -152,6 +152,57 @@ k_rosenbrock_probe(RosenProbeOp<S> op, const double *step_dev, int64_t n, Reduce
     grid_reduce<4>(acc, ws, out);
 }
 
+// Several write-free trials in ONE pass (lbfgsb200_probe_multi_fn).  A More-Thuente search whose trial is still far
+// short of the minimum extrapolates: the next step is stp + 4 (stp - stx) for as long as the interval is not bracketed
+// (src/line.rs:266,  update_trial_interval's clamp to tmax) — a sequence the driver can write down BEFORE the first
+// result is back (with the reference's step cap of |step * d| <= 1 the first trial is short by construction once
+// |x* - x| >> 1: the headline workload takes the steps s, 5 s, 21 s, 85 s in every iteration).  K trial points cost one
+// read of xp and d instead of K: the pass becomes FP64-bound (25 operations per 32 bytes and step) instead of
+// HBM-bound.  Per step the arithmetic, the tile shape and the order of every sum are those of k_rosenbrock_probe, so
+// each of the K results has the bits the single probe would have produced; the line search consumes them only if it
+// asks for exactly those steps.  out = K x {f, g.d, g.g, x.x}, then the K steps used.
+template <bool S, int K>
+struct RosenProbeMultiOp {
+    const double *xp, *d;
+    double step[K];
+    struct Regs { double2 xp, d; };
+    __device__ __forceinline__ void load(Regs &r, int64_t i) const {
+        r.xp = ld2<S>(xp, i);
+        r.d = ld2<S>(d, i);
+    }
+    __device__ __forceinline__ void apply(Regs &r, int64_t, double (&acc)[4 * K]) const {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double2 xo, o;
+            rosen_trial_pair(r.xp, r.d, step[k], xo, o, reinterpret_cast<double (&)[4]>(acc[4 * k]));
+        }
+    }
+    __device__ __forceinline__ void tail(int64_t, double (&)[4 * K]) const {}
+};
+template <bool S, int K>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+k_rosenbrock_probe_multi(RosenProbeMultiOp<S, K> op, const double *step_dev, int64_t n, ReduceWs ws, double *out) {
+    if (step_dev) {   // the chain is formed here from the device's first step, with the line search's own expression
+        double stx = 0.0, stp = __ldcg(step_dev);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            op.step[k] = stp;
+            const double next = stp + 4.0 * (stp - stx);    // src/line.rs:266 (stmax; the clamp of update_trial_interval)
+            stx = stp;
+            stp = next;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[4 * K + k] = op.step[k];
+    }
+    double acc[4 * K];
+#pragma unroll
+    for (int a = 0; a < 4 * K; ++a) acc[a] = 0.0;
+    stream_pairs<4 * K, kUt>(n, op, acc);
+    grid_reduce<4 * K>(acc, ws, out);
+}
+
 // Accepted point + history update in one pass (lbfgsb200_commit_fn): x = xp + step*d and g = grad f(x) are
 // recomputed with the probe's arithmetic (same bits as the accepted probe saw), written once, and
 // s = x - xp, y = g - gp and IterationData::update's sums come out of the same registers — replacing the last
@@ -969,6 +1020,52 @@ int probe_impl(Objective *o, const double *xp, const double *d, double step, con
     return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
 }
 
+template <int K>
+int probe_multi_launch(Objective *o, const double *xp, const double *d, const double *steps, const double *step_dev, int64_t n,
+                       cudaStream_t stream, double *out) {
+    const int grid = stream_grid(o, n, kUt);
+    const int threads = o->sequential ? 1 : kThreads;
+    ReduceWs ws = fused_ws(o);
+    ws.partials = o->wide_partials;   // 4 K rows
+    if (rosen_streaming(o, n)) {
+        RosenProbeMultiOp<true, K> op{xp, d, {}};
+        for (int k = 0; k < K; ++k) op.step[k] = steps ? steps[k] : 0.0;
+        k_rosenbrock_probe_multi<true, K><<<grid, threads, 0, stream>>>(op, step_dev, n, ws, out);
+    } else {
+        RosenProbeMultiOp<false, K> op{xp, d, {}};
+        for (int k = 0; k < K; ++k) op.step[k] = steps ? steps[k] : 0.0;
+        k_rosenbrock_probe_multi<false, K><<<grid, threads, 0, stream>>>(op, step_dev, n, ws, out);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : LBFGSB200_ERR_CUDA;
+}
+
+inline int ensure_wide_partials(Objective *o) {
+    if (o->wide_partials) return 0;
+    if (cudaMalloc((void **)&o->wide_partials, sizeof(double) * (size_t)(5 * kCompactGroupMax + 7) * (size_t)o->ws.stride) != cudaSuccess) {
+        o->wide_partials = nullptr;
+        cudaGetLastError();
+        return LBFGSB200_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+// k trial points in one pass: steps[0 .. k) from the host, or (step_dev != null) the extrapolation chain formed on the
+// device from *step_dev.  k <= 4 on one GPU; with the peer exchange in the epilogue 4 k sums must fit one mailbox entry.
+int probe_multi_impl(Objective *o, const double *xp, const double *d, const double *steps, const double *step_dev, int k,
+                     int64_t n, cudaStream_t stream, double *out) {
+    if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
+    if (k < 1 || k > 4 || (!steps && !step_dev) || (sums_over_ranks(o) && 4 * k > kMailVals)) return LBFGSB200_ERR_INVALID_PARAM;
+    if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
+    if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
+    if (ensure_wide_partials(o) != 0) return LBFGSB200_ERR_UNSUPPORTED;
+    switch (k) {
+        case 1: return probe_multi_launch<1>(o, xp, d, steps, step_dev, n, stream, out);
+        case 2: return probe_multi_launch<2>(o, xp, d, steps, step_dev, n, stream, out);
+        case 3: return probe_multi_launch<3>(o, xp, d, steps, step_dev, n, stream, out);
+        default: return probe_multi_launch<4>(o, xp, d, steps, step_dev, n, stream, out);
+    }
+}
+
 int commit_impl(Objective *o, const double *xp, const double *d, const double *gp, double step, double bs_scale,
                 double *x, double *g, double *s, double *y, int64_t n, cudaStream_t stream, double *out) {
     if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
@@ -1022,12 +1119,7 @@ int commit_gram_impl(Objective *o, const double *xp, const double *d, double ste
     // always rank-local partials (5 n_old + 7 sums do not fit one mailbox entry): the solver sums them over the ranks
     if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
-    if (!o->wide_partials &&
-        cudaMalloc((void **)&o->wide_partials, sizeof(double) * (size_t)(5 * kCompactGroupMax + 7) * (size_t)o->ws.stride) != cudaSuccess) {
-        o->wide_partials = nullptr;
-        cudaGetLastError();
-        return LBFGSB200_ERR_UNSUPPORTED;   // the caller runs commit + pass A separately
-    }
+    if (ensure_wide_partials(o) != 0) return LBFGSB200_ERR_UNSUPPORTED;   // the caller runs commit + pass A separately
 #define LB_CG(G) commit_gram_launch<G>(o, xp, d, step, bs_scale, x, g, s, y, s_old, y_old, n, stream, hist, gram_out, newdot_out)
     switch (n_old) {
         case 0: return LB_CG(0);
@@ -1232,6 +1324,12 @@ int lbfgsb200_objective_commit(void *objective, const double *xp_dev, const doub
     return lb::commit_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, gp_dev, step, bs_scale, x_dev, g_dev,
                            s_dev, y_dev, n_local, (cudaStream_t)stream, out_dev);
 }
+int lbfgsb200_objective_probe_multi(void *objective, const double *xp_dev, const double *d_dev, const double *steps,
+                                    const double *step0_dev, int k, int64_t n_local, void *stream, double *out_dev) {
+    if (!objective || !xp_dev || !d_dev || !out_dev) return LBFGSB200_ERR_INVALID_PARAM;
+    return lb::probe_multi_impl(reinterpret_cast<lb::Objective *>(objective), xp_dev, d_dev, steps, step0_dev, k, n_local,
+                                (cudaStream_t)stream, out_dev);
+}
 int lbfgsb200_objective_commit_gram(void *objective, const double *xp_dev, const double *d_dev, const double *gp_dev, double step,
                                     double bs_scale, double *x_dev, double *g_dev, double *s_dev, double *y_dev,
                                     const double *const *s_old_dev, const double *const *y_old_dev, int n_old, int64_t n_local,
@@ -1252,6 +1350,7 @@ int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fu
     out->probe = nullptr;
     out->commit = nullptr;
     out->commit_gram = nullptr;
+    out->probe_multi = nullptr;
     out->user = o;
     out->flags = 0;
     if (o->kind == lb::OBJ_ROSENBROCK) {
@@ -1259,6 +1358,7 @@ int lbfgsb200_objective_fused_ops(lbfgsb200_objective_t *objective, lbfgsb200_fu
         out->probe = lbfgsb200_objective_probe;
         out->commit = lbfgsb200_objective_commit;
         if (o->recompute_gp) out->commit_gram = lbfgsb200_objective_commit_gram;
+        out->probe_multi = lbfgsb200_objective_probe_multi;
         if (lb::sums_over_ranks(o)) out->flags |= LBFGSB200_FUSED_SUMS_OVER_RANKS;
         if (o->recompute_gp) out->flags |= LBFGSB200_FUSED_COMMIT_SKIPS_GP;
     }

@@ -107,7 +107,7 @@ int scratch_acquire(const DeviceInfo &dev, size_t scal_count, Scratch *out) {
     s.device = dev.device;
     s.scal_count = scal_count < 256 ? 256 : scal_count;   // room for alpha[m] up to m ~ 200 without a re-allocation
     if (cudaMalloc((void **)&s.scal_dev, sizeof(double) * s.scal_count) != cudaSuccess ||
-        cudaMallocHost((void **)&s.scal_host, sizeof(double) * 64) != cudaSuccess ||   // Solver::kHostWords
+        cudaMallocHost((void **)&s.scal_host, sizeof(double) * 128) != cudaSuccess ||   // Solver::kHostWords
         alloc_reduce_ws(dev, &s.ws) != 0) {
         scratch_free(s);
         return LBFGSB200_ERR_CUDA;
@@ -320,6 +320,9 @@ int Solver::init(const lbfgsb200_param_t &p, int64_t n_local, int64_t n_global, 
     small_enabled_ = env_int("LBFGSB200_SMALL", 1) != 0;
     speculate_ = env_int("LBFGSB200_SPECULATE", 1) != 0;
     commit_gram_enabled_ = env_int("LBFGSB200_COMMIT_GRAM", 1) != 0;
+    multi_probe_max_ = env_int("LBFGSB200_MULTI_PROBE_MAX", kSpecMax);
+    if (multi_probe_max_ < 1) multi_probe_max_ = 1;
+    if (multi_probe_max_ > kSpecMax) multi_probe_max_ = kSpecMax;
     ring_stride_ = vec_bytes / (int64_t)sizeof(double);
     // process-wide default (lbfgsb200_set_default_direction, else LBFGSB200_DIRECTION=compact); lbfgsb200_set_direction wins
     int dflt = g_default_direction.load();
@@ -580,6 +583,34 @@ bool Solver::trial_point(const double *xp, double stp, double *dg_out) {
     return evaluate_point(d_, dg_out);
 }
 
+int Solver::multi_probe_cap() const {
+    if (!use_probe() || !fused_.probe_multi || multi_probe_max_ < 2) return 1;
+    const bool multi = comm_ && comm_size(comm_) > 1;
+    if (!multi) return multi_probe_max_;
+    if (!fused_exchanges()) return 1;                      // rank-local partials would need an exchange of 4 k values
+    const int fit = kMailVals / 4;                          // 4 sums per trial point in one mailbox entry
+    return multi_probe_max_ < fit ? multi_probe_max_ : fit;
+}
+
+// steps[0] is the trial the search asked for; steps[1 .. k) are the ones it will ask for if it keeps extrapolating.
+bool Solver::trial_multi(const double *xp, const double *steps, int k, Speculation *sp) {
+    const double vbytes = 8.0 * (double)n_;
+    prof_begin(LBFGSB200_K_PROBE);
+    const int erc = fused_.probe_multi(fused_.user, xp, d_, steps, nullptr, k, n_, (void *)stream_, slot(SLOT_SPEC));
+    prof_end(LBFGSB200_K_PROBE, 2.0 * vbytes);
+    launch_counter_ += 1;
+    if (erc != 0) return false;                             // single GPU, or "fails on every rank or on none"
+    double h[5 * kSpecMax];
+    if (last_status_ <= LBFGSB200_ERR_CUDA) return false;
+    if (fetch(SLOT_SPEC, 5 * k, h, /*ours=*/true) != 0) return false;
+    sp->count = k;
+    for (int i = 0; i < k; ++i) {
+        sp->step[i] = h[4 * k + i];
+        for (int j = 0; j < 4; ++j) sp->h[i][j] = h[4 * i + j];
+    }
+    return true;
+}
+
 void Solver::fill_progress(lbfgsb200_progress_t *out, double step_value) const {  // core.rs:253-268
     if (!out) return;
     out->x_dev = xbuf_[cur_x_];
@@ -616,7 +647,8 @@ int Solver::build(double *x_dev, lbfgsb200_eval_fn eval, void *user) {
     last_status_ = 0;
     err_.clear();
     built_ = false;
-    spec_.valid = false;
+    spec_.count = 0;
+    spec_k_ = 1;
 
     if (!evaluate_point(nullptr, nullptr)) {  // :454
         if (last_status_ != 0) return last_status_;
@@ -992,23 +1024,43 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     double stp = 0.0, stp_eval = 0.0;   // stp_eval: the step of the last EVALUATED trial, i.e. where x is (line.rs:396-398
                                         // leaves `stp` one update ahead when the search runs out of trials)
     Speculation spec = spec_;
-    spec_.valid = false;
+    spec_.count = 0;
+    const int cap = multi_probe_cap();
     while (ls.next_trial(&stp)) {
         double dg = 0.0;
         stp_eval = stp;
         bool ok;
-        if (spec.valid && spec.step == stp && use_probe()) {
-            // this trial was probed behind the previous update and came back with its scalars: no launch, no round trip
+        int hit = -1;
+        if (use_probe())
+            for (int i = 0; i < spec.count; ++i)
+                if (spec.step[i] == stp) hit = i;
+        if (hit < 0 && cap > 1 && spec_k_ > (int)ls.trials()) {   // (a search that outlives the guess goes on one trial at a time)
+            // one pass for this trial and the ones the search is expected to ask for next (as many as the previous search
+            // needed): they share the read of xp and d
+            double steps[kSpecMax] = {stp, 0.0, 0.0, 0.0};
+            int want = spec_k_ - ((int)ls.trials() - 1);     // trials() counts the one just handed out
+            if (want > cap) want = cap;
+            const int k = 1 + ls.predict(steps + 1, want - 1);
+            spec.count = 0;
+            if (k > 1) {
+                if (trial_multi(xp, steps, k, &spec)) hit = 0;
+                else if (last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;
+                else spec.count = 0;                        // the objective declined: probe this trial alone below
+            }
+        }
+        if (hit >= 0) {
+            // this trial was probed ahead — behind the previous update, or in the same pass as an earlier trial — and came
+            // back with its scalars: no launch, no round trip
             neval_ += 1;
-            fx_ = spec.h[0];
-            dg = spec.h[1];
-            gg_ = spec.h[2];
-            xx_ = spec.h[3];
+            fx_ = spec.h[hit][0];
+            dg = spec.h[hit][1];
+            gg_ = spec.h[hit][2];
+            xx_ = spec.h[hit][3];
             ok = true;
         } else {
+            spec.count = 0;
             ok = trial_point(xp, stp, &dg);
         }
-        spec.valid = false;
         if (!ok && last_status_ <= LBFGSB200_ERR_CUDA) return last_status_;  // CUDA / NCCL failure is fatal
         ls.feed(ok, fx_, dg);
     }
@@ -1025,6 +1077,7 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         return fail(LBFGSB200_ERR_X_NOT_CHANGED, msg);
     }
     ncall_ = ls.ncall();
+    spec_k_ = ncall_ < 1 ? 1 : (ncall_ > kSpecMax ? kSpecMax : (int)ncall_);   // what the next search will probably need
 
     // IterationData::update (src/lbfgs.rs:640-692) + lbfgs_two_loop_recursion (:569-604): 1 + 2*bound kernels with no
     // host round trip in between.  In the launch-bound regime (small n, steady state) the chain is captured once
@@ -1049,11 +1102,20 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
     // round trip instead of two.  Unused (the solve stops, the search wants another first step) it is just dropped.
     const bool multi = comm_ && comm_size(comm_) > 1;
     bool speculated = false;
+    int spec_multi = 0;   // trial points of the speculative pass when it went through the multi-step probe
     if (speculate_ && use_probe() && (!multi || fused_exchanges())) {
         if (!small_ran)   // (the cluster kernel forms the step in its own epilogue)
             launch_next_step(L, slot(so_last), p_.max_step_size, p_.constrain_step_size != 0, slot(SLOT_STEP));
+        int kq = spec_k_ < cap ? spec_k_ : cap;
+        if (!ls.uses_morethuente()) kq = 1;                 // the chain is More-Thuente's extrapolation
         prof_begin(LBFGSB200_K_PROBE);
-        const int erc = fused_.probe(fused_.user, xbuf_[cur_x_], d_, 0.0, slot(SLOT_STEP), n_, (void *)stream_, slot(SLOT_EVAL));
+        int erc;
+        if (kq > 1) {
+            erc = fused_.probe_multi(fused_.user, xbuf_[cur_x_], d_, nullptr, slot(SLOT_STEP), kq, n_, (void *)stream_, slot(SLOT_SPEC));
+            spec_multi = erc == 0 ? kq : 0;
+        } else {
+            erc = fused_.probe(fused_.user, xbuf_[cur_x_], d_, 0.0, slot(SLOT_STEP), n_, (void *)stream_, slot(SLOT_EVAL));
+        }
         prof_end(LBFGSB200_K_PROBE, 2.0 * vbytes);
         launch_counter_ += 1;
         speculated = erc == 0;
@@ -1067,9 +1129,18 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         if (rc != 0) return rc;
         for (int i = 0; i < 5; ++i) h[i] = hall[SLOT_HIST * kMaxAcc + i];
         for (int i = 0; i < 3; ++i) hd[i] = hall[so_last * kMaxAcc + i];
-        next_spec.valid = true;
-        next_spec.step = hall[SLOT_STEP * kMaxAcc];
-        for (int i = 0; i < 4; ++i) next_spec.h[i] = hall[SLOT_EVAL * kMaxAcc + i];
+        if (spec_multi > 0) {
+            const double *q = hall + SLOT_SPEC * kMaxAcc;
+            next_spec.count = spec_multi;
+            for (int i = 0; i < spec_multi; ++i) {
+                next_spec.step[i] = q[4 * spec_multi + i];
+                for (int j = 0; j < 4; ++j) next_spec.h[i][j] = q[4 * i + j];
+            }
+        } else {
+            next_spec.count = 1;
+            next_spec.step[0] = hall[SLOT_STEP * kMaxAcc];
+            for (int i = 0; i < 4; ++i) next_spec.h[0][i] = hall[SLOT_EVAL * kMaxAcc + i];
+        }
     } else {
         rc = fetch2(SLOT_HIST, 5, h, so_last, 3, hd);
         if (rc != 0) return rc;

@@ -76,9 +76,9 @@ class Solver {
         fused_ = lbfgsb200_fused_ops_t{};
         fused_.trial = fn;
         fused_.user = user;
-        spec_.valid = false;
+        spec_.count = 0;
     }
-    void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; spec_.valid = false; }
+    void set_fused_ops(const lbfgsb200_fused_ops_t *ops) { fused_ = ops ? *ops : lbfgsb200_fused_ops_t{}; spec_.count = 0; }
 
     // LBFGSB200_DIRECTION_*: how the search direction is formed (before build(); compact needs m <= kCompactMaxM)
     int set_direction(int mode);
@@ -90,17 +90,23 @@ class Solver {
     void profile_reset();
 
   private:
+    struct Speculation;
     // scalar slots in device memory (kMaxAcc doubles each)
     // SLOT_STEP[0]: the next search's first step as formed on the device (speculative first trial)
-    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_STEP = 5, SLOT_COUNT = 6 };
-    static constexpr int kHostWords = 64;       // pinned mirror: every slot (48 doubles) + the evaluate-flag staging word
-    static constexpr int kFlagWord = 56;
+    // SLOT_SPEC .. SLOT_SPEC + 2: the results of a multi-step probe, kSpecMax x {f, g.d, g.g, x.x} then the steps used
+    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_STEP = 5, SLOT_SPEC = 6, SLOT_COUNT = 9 };
+    static constexpr int kSpecMax = 4;          // trial points per multi-step probe (5 * kSpecMax doubles <= 3 slots)
+    static constexpr int kHostWords = 128;      // pinned mirror: every slot (72 doubles) + the evaluate-flag staging word
+    static constexpr int kFlagWord = 120;
     double *slot(int s) const { return scal_dev_ + (size_t)s * kMaxAcc; }
 
     int fail(int status, const char *msg);
     int cuda_fail(cudaError_t e, const char *what);
     bool evaluate_point(const double *d_or_null, double *dg_out);  // evaluate + K2/K3 + allreduce + sync
     bool trial_point(const double *xp, double stp, double *dg_out); // K1 + evaluate_point, or the fused callbacks
+    // one pass for the trial at steps[0] AND the k - 1 predicted ones after it; fills `sp` with all k results
+    bool trial_multi(const double *xp, const double *steps, int k, Speculation *sp);
+    int multi_probe_cap() const;  // how many trial points a pass may carry here (1: the multi-step probe is unavailable)
     // allreduce (unless `exchanged`: the producer already summed over the ranks) + D2H + sync of SLOT_EVAL
     bool finish_eval(bool fused, bool exchanged, double *dg_out);
     bool use_probe() const { return fused_.probe && fused_.commit && !owl_; }
@@ -169,7 +175,11 @@ class Solver {
     // The next iteration's first trial, probed speculatively behind the two-loop recursion (write-free, so harmless
     // if it is never used): its step and {f, g.d, g.g, x.x}.  Consumed by the next propagate() if the line search
     // asks for exactly that step.
-    struct Speculation { bool valid = false; double step = 0.0; double h[4] = {0.0, 0.0, 0.0, 0.0}; } spec_;
+    // With the objective's multi-step probe the trials the search is EXPECTED to take next (More-Thuente's extrapolation
+    // chain, LineSearchMachine::predict) ride in the same pass: up to kSpecMax entries.
+    struct Speculation { int count = 0; double step[4] = {0.0, 0.0, 0.0, 0.0}; double h[4][4] = {}; } spec_;
+    int spec_k_ = 1;              // trial points to evaluate per pass: what the previous search needed (adaptive)
+    int multi_probe_max_ = 4;     // LBFGSB200_MULTI_PROBE_MAX (1 disables)
     bool speculate_ = true;       // LBFGSB200_SPECULATE=0 disables
     bool built_ = false;
     double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point

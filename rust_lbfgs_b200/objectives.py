@@ -51,6 +51,7 @@ class _Builtin:
             ops.probe = None
             ops.commit = None
             ops.commit_gram = None
+            ops.probe_multi = None
         if not (ops.trial or ops.probe):
             return None
         return ops

@@ -120,7 +120,12 @@ pub type lbfgsb200_commit_gram_fn = Option<unsafe extern "C" fn(user: *mut c_voi
     s_old_dev: *const *const f64, y_old_dev: *const *const f64, n_old: c_int, n_local: i64, stream: *mut c_void,
     out_dev: *mut f64, gram_out_dev: *mut f64, newdot_out_dev: *mut f64) -> c_int>;
 
+/// Several write-free trials in one pass (include/lbfgsb200.h: lbfgsb200_probe_multi_fn).
+pub type lbfgsb200_probe_multi_fn = Option<unsafe extern "C" fn(user: *mut c_void, xp_dev: *const f64, d_dev: *const f64,
+    steps: *const f64, step0_dev: *const f64, k: c_int, n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int>;
+
 pub const LBFGSB200_FUSED_OPS_SIZE_V1: i64 = 48;
+pub const LBFGSB200_FUSED_OPS_SIZE_V2: i64 = 56;
 pub const LBFGSB200_FUSED_SUMS_OVER_RANKS: i64 = 1;
 pub const LBFGSB200_FUSED_COMMIT_SKIPS_GP: i64 = 2;
 /// `lbfgsb200_fused_ops_t`: what an objective offers beyond evaluate.
@@ -134,11 +139,12 @@ pub struct lbfgsb200_fused_ops_t {
     pub user: *mut c_void,
     pub flags: i64,
     pub commit_gram: lbfgsb200_commit_gram_fn,
+    pub probe_multi: lbfgsb200_probe_multi_fn,
 }
 impl Default for lbfgsb200_fused_ops_t {
     fn default() -> Self {
         Self { struct_size: std::mem::size_of::<Self>() as i64, trial: None, probe: None, commit: None, user: std::ptr::null_mut(), flags: 0,
-               commit_gram: None }
+               commit_gram: None, probe_multi: None }
     }
 }
 
@@ -240,6 +246,9 @@ extern "C" {
     pub fn lbfgsb200_objective_commit(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
                                       bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
                                       n_local: i64, stream: *mut c_void, out_dev: *mut f64) -> c_int;
+    pub fn lbfgsb200_objective_probe_multi(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, steps: *const f64,
+                                           step0_dev: *const f64, k: c_int, n_local: i64, stream: *mut c_void,
+                                           out_dev: *mut f64) -> c_int;
     pub fn lbfgsb200_objective_commit_gram(objective: *mut c_void, xp_dev: *const f64, d_dev: *const f64, gp_dev: *const f64, step: f64,
                                            bs_scale: f64, x_dev: *mut f64, g_dev: *mut f64, s_dev: *mut f64, y_dev: *mut f64,
                                            s_old_dev: *const *const f64, y_old_dev: *const *const f64, n_old: c_int, n_local: i64,
@@ -252,6 +261,7 @@ extern "C" {
     pub fn lbfgsb200_linesearch_begin(param: *const lbfgsb200_param_t, orthantwise: c_int, finit: f64, dginit: f64, step: f64)
         -> *mut lbfgsb200_linesearch_t;
     pub fn lbfgsb200_linesearch_next(ls: *mut lbfgsb200_linesearch_t, step_out: *mut f64) -> c_int;
+    pub fn lbfgsb200_linesearch_predict(ls: *const lbfgsb200_linesearch_t, steps_out: *mut f64, kmax: c_int) -> c_int;
     pub fn lbfgsb200_linesearch_feed(ls: *mut lbfgsb200_linesearch_t, eval_ok: c_int, f: f64, dg: f64);
     pub fn lbfgsb200_linesearch_result(ls: *mut lbfgsb200_linesearch_t, ncall: *mut i64, step: *mut f64) -> c_int;
     pub fn lbfgsb200_linesearch_end(ls: *mut lbfgsb200_linesearch_t);

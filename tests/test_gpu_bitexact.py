@@ -328,6 +328,8 @@ def test_speculative_first_trial_is_transparent(monkeypatch):
             x0 = perturbed_x0(n, seed=5)
             _same_traces(run(True, builder, x0), run(False, builder, x0), f"{name} n={n}")
     # and it does save the round trip: host synchronisations per iteration = evaluations, not evaluations + 1
+    # (one trial point per pass here: test_multi_step_probe_is_transparent covers several)
+    monkeypatch.setenv("LBFGSB200_MULTI_PROBE_MAX", "1")
     syncs = {}
     for spec in (True, False):
         monkeypatch.setenv("LBFGSB200_SPECULATE", "1" if spec else "0")
@@ -340,3 +342,47 @@ def test_speculative_first_trial_is_transparent(monkeypatch):
         syncs[spec] = (st.profile()["host_syncs"], evals)
         st.close()
     assert syncs[False][0] == syncs[False][1] + 20 and syncs[True][0] <= syncs[True][1] + 1, syncs
+
+
+def test_multi_step_probe_is_transparent(monkeypatch):
+    """Several line-search trials per pass (lbfgsb200_probe_multi_fn): the steps More-Thuente is EXPECTED to take next —
+    its extrapolation chain stp + 4 (stp - stx), as many as the previous search needed — are evaluated in the same read
+    of xp and d, and a result is used only when the search then asks for exactly that step.  Same bits with 1, 2, 3, 4
+    trial points per pass: every line search (the backtracking ones never predict), step-size caps that make the chain
+    long or make it miss, reference-order sums; and far fewer passes where the search extrapolates."""
+    import torch
+
+    def run(kmax, builder, x0):
+        monkeypatch.setenv("LBFGSB200_MULTI_PROBE_MAX", str(kmax))
+        return gpu_minimize(builder(), x0, R.Rosenbrock())
+    for name, builder in (
+            ("MoreThuente", lambda: R.lbfgs().with_max_iterations(40)),
+            ("m = 20", lambda: R.lbfgs().with_m(20).with_max_iterations(40)),
+            ("Armijo + damping", lambda: R.lbfgs().with_linesearch_algorithm("BacktrackingArmijo").with_damping(True).with_max_iterations(40)),
+            ("tight step-size cap (long chains)", lambda: R.lbfgs().with_max_step_size(0.05).with_max_iterations(25)),
+            ("no step-size cap (chains miss)", lambda: R.lbfgs().with_max_step_size(1e20).with_max_iterations(40)),
+            ("max_linesearch = 3", lambda: R.lbfgs().with_max_linesearch(3).with_max_iterations(25)),
+            ("compact direction", lambda: R.lbfgs().with_direction("compact").with_max_iterations(40)),
+            ("sequential sums", lambda: seq().with_max_iterations(30))):
+        for n in (100, 5000, 300_000):
+            x0 = perturbed_x0(n, seed=5)
+            ref = run(1, builder, x0)
+            for kmax in (2, 3, 4):
+                _same_traces(run(kmax, builder, x0), ref, f"{name} n={n} kmax={kmax}")
+    # the headline pattern (every search takes s, 5 s, 21 s, ...): passes per iteration drop from ~3.5 to ~1
+    passes = {}
+    for kmax in (1, 4):
+        monkeypatch.setenv("LBFGSB200_MULTI_PROBE_MAX", str(kmax))
+        x = torch.empty(1_000_000, dtype=torch.float64, device="cuda:0")
+        x[0::2], x[1::2] = -1.2, 1.0
+        st = R.lbfgs().build(x, R.Rosenbrock())
+        st.propagate()
+        st.profile_reset()
+        evals = 0
+        for _ in range(20):
+            evals += st.propagate().ncall
+        passes[kmax] = (st.profile()["launches"]["probe"], evals)
+        st.close()
+    monkeypatch.delenv("LBFGSB200_MULTI_PROBE_MAX")
+    assert passes[1][1] == passes[4][1] and passes[1][0] >= passes[1][1], passes
+    assert passes[4][0] <= 0.5 * passes[1][0], passes

@@ -28,6 +28,9 @@ def quartic(x, g):
     return float(np.sum(x ** 4 - np.sin(3.0 * x)))
 
 
+PREDICT_STATS = None   # set by test_predictions_* to collect how often lbfgsb200_linesearch_predict was right
+
+
 def run_case(oracle, fn, x0, d, step0, algo, gradient_only=False, max_ls=20, owl_flag=False, gtol=0.9, ftol=1e-4):
     calls = []
 
@@ -56,8 +59,21 @@ def run_case(oracle, fn, x0, d, step0, algo, gradient_only=False, max_ls=20, owl
     assert h
     stp = C.c_double()
     k = 0
+    pending = []      # predictions made at earlier trials for the trial now handed out
     while L.lbfgsb200_linesearch_next(h, C.byref(stp)):
         assert k < len(trials), "product asked for more trials than the oracle evaluated"
+        # predict() is pure (the replay below stays identical to the oracle's) and never wrong when the search does
+        # extrapolate: a step above every earlier one, with the interval not bracketed, IS the predicted one
+        if PREDICT_STATS is not None:
+            if pending:
+                PREDICT_STATS["made"] += 1
+                PREDICT_STATS["hit"] += int(pending[0] == stp.value)
+            buf = (C.c_double * 3)()
+            cnt = L.lbfgsb200_linesearch_predict(h, buf, 3)
+            new = [buf[i] for i in range(cnt)]
+            if pending and pending[0] == stp.value and len(pending) > 1 and new:
+                assert pending[1] == new[0], (pending, new)      # a chain predicted earlier stays the chain
+            pending = new
         x_ref, f, g = trials[k]
         x_mine = x0 + stp.value * d            # veccpy + vecadd, src/core.rs:156-157
         assert np.array_equal(x_mine, x_ref), (k, stp.value)
@@ -180,3 +196,44 @@ def test_machine_replays_oracle_on_pathological_values(oracle, algo):
             assert k == len(calls) - 1, (algo, k_bad, kind)
             assert (err, ncall.value) == (ref["ls_error"], ref["ncall"]), (algo, k_bad, kind, err, ref)
             assert step.value == ref["step"] or (np.isnan(step.value) and np.isnan(ref["step"])), (algo, k_bad, kind)
+
+
+def test_predictions_are_the_extrapolation_chain_and_change_nothing(oracle):
+    """lbfgsb200_linesearch_predict: on a search that keeps extrapolating (f decreasing along d for a long way, first
+    step tiny) the predicted steps are exactly the ones asked for — s, 5 s, 21 s, 85 s — and on random searches calling
+    it between next and feed leaves the replay identical to the oracle's (run_case asserts that) while a good share of
+    the predictions come true."""
+    global PREDICT_STATS
+    L = R.lib()
+    pp = R.default_param()
+    h = L.lbfgsb200_linesearch_begin(C.byref(pp), 0, 0.0, -1.0, 1e-3)       # phi(t) = -t + 1e-9 t^2: minimum at 5e8
+    stp, seen, buf = C.c_double(), [], (C.c_double * 3)()
+    for _ in range(6):
+        assert L.lbfgsb200_linesearch_next(h, C.byref(stp))
+        seen.append(stp.value)
+        cnt = L.lbfgsb200_linesearch_predict(h, buf, 3)
+        assert cnt == 3
+        pred = [buf[i] for i in range(3)]
+        if len(seen) >= 2:
+            assert seen[-1] == last_pred[0] and pred[0] == last_pred[1] and pred[1] == last_pred[2]
+        last_pred = pred
+        t = stp.value
+        L.lbfgsb200_linesearch_feed(h, 1, -t + 1e-9 * t * t, -1.0 + 2e-9 * t)
+    L.lbfgsb200_linesearch_end(h)
+    assert [round(s / seen[0]) for s in seen] == [1, 5, 21, 85, 341, 1365]
+    PREDICT_STATS = {"made": 0, "hit": 0}
+    try:
+        rng = np.random.default_rng(99)
+        for trial in range(200):
+            n = 10
+            fn = rosen if trial % 2 == 0 else quartic
+            x0 = rng.uniform(-2.0, 2.0, n)
+            g = np.zeros(n)
+            fn(x0, g)
+            d = -g
+            step0 = float(10.0 ** rng.uniform(-6, -2)) / max(np.linalg.norm(d), 1e-300)   # short first steps: searches that extrapolate
+            run_case(oracle, fn, x0, d, step0, 0)
+        stats = dict(PREDICT_STATS)
+    finally:
+        PREDICT_STATS = None
+    assert stats["made"] > 200 and stats["hit"] > 0.5 * stats["made"], stats
