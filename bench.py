@@ -110,13 +110,13 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes_survey(n, launches, kbytes):
-    # evaluations = unfused evaluate callbacks + fused trial evaluations
+def algorithmic_bytes_survey(n, launches, kbytes, evaluations=None):
+    # evaluations = unfused evaluate callbacks + fused trial evaluations (several may share one probe pass)
     """per iteration (6t + 6 + 8b) V solver-only + 2V t for the Rosenbrock evaluate,
     V = 8n bytes: trial step 3V t + post-eval dots 3V t + history update 7V + two-loop (8b - 1) V.
     t and b are the MEASURED evaluation / two-loop trip counts of the timed region."""
     V = 8.0 * n
-    t = launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)
+    t = evaluations if evaluations is not None else launches["evaluate"] + launches.get("trial_eval", 0) + launches.get("probe", 0)
     iters = launches["history"] + launches.get("commit", 0)
     return 8.0 * t * V + 7.0 * iters * V + kbytes["backward"] + kbytes["forward"]
 
@@ -406,7 +406,8 @@ def compact_block(R, D, dev, comm, world, rank, n_local, m, K, W, fused, barrier
         "algorithmic_bytes_per_iteration_per_gpu": moved / max(1, K),
         "algorithmic_GBps_per_gpu": moved / 1e9 / (r["ms_total"] / 1e3),
         "frac_of_peak_per_gpu": moved / 1e9 / (r["ms_total"] / 1e3) / peak,
-        "evaluations_per_iteration": evals / max(1, K),
+        "evaluations_per_iteration": sum(t[1] for t in r["seen"]) / max(1, K),
+        "line_search_passes_per_iteration": evals / max(1, K),
         "direction_kernel_GBps": (kbytes["forward"] / 1e9) / (kms["forward"] / 1e3) if kms["forward"] > 0 else None,
         "profile_pass_kernel_GBps": {names.get(k, k): round(pa["bytes"][k] / 1e9 / (pa["ms"][k] / 1e3), 1) for k in pa["ms"]
                                      if pa["ms"][k] > 0 and pa["bytes"][k] > 0},
@@ -485,7 +486,7 @@ def run_ours(args):
         "launches": int(launches[DOM]), "avg_launch_ms": kms[DOM] / max(1, launches[DOM]),
         "algorithmic_bytes_per_launch": kbytes[DOM] / max(1, launches[DOM]),
     }
-    surv_bytes = algorithmic_bytes_survey(n_local, launches, kbytes)
+    surv_bytes = algorithmic_bytes_survey(n_local, launches, kbytes, evaluations=sum(t[1] for t in seen))
     pa = r["prof_all"]
     iteration = {
         # bytes the launched kernels must move (DESIGN.md §3 per-kernel passes x 8n) / wall time of the K steps
@@ -498,7 +499,9 @@ def run_ours(args):
         "survey_formula_equivalent_GBps_per_gpu": surv_bytes / 1e9 / (ms_total / 1e3),
         "line_search_trials": ("probe + commit" if launches.get("probe", 0) > 0 else
                                "fused trial" if launches.get("trial_eval", 0) > 0 else "unfused (K1 + evaluate + K2)"),
-        "evaluations_per_iteration": evals / max(1, K),
+        "evaluations_per_iteration": sum(t[1] for t in seen) / max(1, K),
+        # several trial points share one pass over xp and d when the search extrapolates (lbfgsb200_probe_multi_fn)
+        "line_search_passes_per_iteration": evals / max(1, K),
         "kernel_ms_timed_region": {k: round(v, 3) for k, v in kms.items() if v > 0},
         "profile_pass": {
             "note": f"{P} extra iterations after the timed region with CUDA events around every launch",
@@ -621,7 +624,8 @@ def run_ours(args):
                 "algorithmic_GBps": moved5 * world / 1e9 / (r5["ms_total"] / 1e3),
                 "algorithmic_GBps_per_gpu": moved5 / 1e9 / (r5["ms_total"] / 1e3),
                 "frac_of_peak_per_gpu": moved5 / 1e9 / (r5["ms_total"] / 1e3) / peak,
-                "evaluations_per_iteration": ev5 / K5,
+                "evaluations_per_iteration": sum(t[1] for t in r5["seen"]) / K5,
+                "line_search_passes_per_iteration": ev5 / K5,
                 "k_backward_GBps": (kb5[DOM] / 1e9) / (km5[DOM] / 1e3) if km5[DOM] > 0 else None,
                 "parity": isometric_parity(r5["seen"], n5 * world, m5, 1 + W5 + K5) if (rank == 0 and not args.no_cpu_baseline) else None,
             }
