@@ -179,8 +179,11 @@ struct RosenProbeMultiOp {
     }
     __device__ __forceinline__ void tail(int64_t, double (&)[4 * K]) const {}
 };
+#ifndef LB_PM_BLOCKS
+#define LB_PM_BLOCKS kMinBlocks   // resident CTAs per SM of the multi-step probe (FP64-bound: tuned separately from the HBM-bound kernels)
+#endif
 template <bool S, int K>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+__global__ void __launch_bounds__(kThreads, LB_PM_BLOCKS)
 k_rosenbrock_probe_multi(RosenProbeMultiOp<S, K> op, const double *step_dev, int64_t n, ReduceWs ws, double *out) {
     if (step_dev) {   // the chain is formed here from the device's first step, with the line search's own expression
         double stx = 0.0, stp = __ldcg(step_dev);

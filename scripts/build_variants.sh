@@ -35,6 +35,7 @@ for v in "$@"; do
     x-*) IFS=- read -r _ u uh ut <<< "$v"; build "$v" "$u" 1 "$uh" 256 "$ut";;   # x-<U>-<UH>-<UT>
     s-*) IFS=- read -r _ ld st <<< "$v"; EXTRA2="-DLB_LD_POLICY=$ld -DLB_ST_POLICY=$st" build "$v" 8 1 4 256 6;;   # s-<LD>-<ST>: cache policies, shipped tiles
     cg-*) IFS=- read -r _ u b <<< "$v"; EXTRA2="-DLB_CG_U=$u -DLB_CG_BLOCKS=$b" build "$v" 8 2 4 256 6;;   # cg-<U>-<CTAs per SM>: commit fused with pass A
+    pm-*) IFS=- read -r _ b <<< "$v"; EXTRA2="-DLB_PM_BLOCKS=$b" build "$v" 8 2 4 256 6;;   # pm-<CTAs per SM>: the multi-step probe
     gram-*) IFS=- read -r _ u <<< "$v"; EXTRA2="-DLB_GRAM_U=$u" build "$v" 8 2 4 256 6;;   # gram-<U>: pass A of the compact direction, 3..5 older pairs
     p-*) IFS=- read -r _ u uh ut <<< "$v"; EXTRA2="-DLB_PROBE_PREFETCH=1" build "$v" "$u" 1 "$uh" 256 "$ut";;   # the same with the prefetching probe
   esac
