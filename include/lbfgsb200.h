@@ -173,7 +173,7 @@ typedef int (*lbfgsb200_commit_gram_fn)(void *user, const double *xp_dev, const 
                                         int n_old, int64_t n_local, void *stream, double *out_dev, double *gram_out_dev,
                                         double *newdot_out_dev);
 
-/* Optional: k <= 4 write-free trials in ONE pass over xp and d.  steps[0 .. k) are host values; with step0_dev != NULL
+/* Optional: k <= 6 write-free trials in ONE pass over xp and d.  steps[0 .. k) are host values; with step0_dev != NULL
  * they are instead the More-Thuente extrapolation chain s_0 = *step0_dev, s_{j+1} = s_j + 4 (s_j - s_{j-1}), s_{-1} = 0
  * (src/line.rs:266), formed on the device with exactly that expression.  out_dev[4 j + 0..3] = { f, g.d, g.g, x.x } at
  * xp + s_j d, each with the bits lbfgsb200_probe_fn would give for that step; out_dev[4 k + j] = s_j.  The solver asks

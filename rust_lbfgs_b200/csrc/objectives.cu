@@ -1053,11 +1053,11 @@ inline int ensure_wide_partials(Objective *o) {
 }
 
 // k trial points in one pass: steps[0 .. k) from the host, or (step_dev != null) the extrapolation chain formed on the
-// device from *step_dev.  k <= 4 on one GPU; with the peer exchange in the epilogue 4 k sums must fit one mailbox entry.
+// device from *step_dev.  k <= 6; with the peer exchange in the epilogue the 4 k sums must fit one mailbox entry.
 int probe_multi_impl(Objective *o, const double *xp, const double *d, const double *steps, const double *step_dev, int k,
                      int64_t n, cudaStream_t stream, double *out) {
     if (o->kind != OBJ_ROSENBROCK) return LBFGSB200_ERR_UNSUPPORTED;
-    if (k < 1 || k > 4 || (!steps && !step_dev) || (sums_over_ranks(o) && 4 * k > kMailVals)) return LBFGSB200_ERR_INVALID_PARAM;
+    if (k < 1 || k > 6 || (!steps && !step_dev) || (sums_over_ranks(o) && 4 * k > kMailVals)) return LBFGSB200_ERR_INVALID_PARAM;
     if (n & 1) return LBFGSB200_ERR_INVALID_PARAM;
     if (cudaSetDevice(o->dev.device) != cudaSuccess) return LBFGSB200_ERR_CUDA;
     if (ensure_wide_partials(o) != 0) return LBFGSB200_ERR_UNSUPPORTED;
@@ -1065,7 +1065,9 @@ int probe_multi_impl(Objective *o, const double *xp, const double *d, const doub
         case 1: return probe_multi_launch<1>(o, xp, d, steps, step_dev, n, stream, out);
         case 2: return probe_multi_launch<2>(o, xp, d, steps, step_dev, n, stream, out);
         case 3: return probe_multi_launch<3>(o, xp, d, steps, step_dev, n, stream, out);
-        default: return probe_multi_launch<4>(o, xp, d, steps, step_dev, n, stream, out);
+        case 4: return probe_multi_launch<4>(o, xp, d, steps, step_dev, n, stream, out);
+        case 5: return probe_multi_launch<5>(o, xp, d, steps, step_dev, n, stream, out);
+        default: return probe_multi_launch<6>(o, xp, d, steps, step_dev, n, stream, out);
     }
 }
 

@@ -1037,7 +1037,8 @@ int Solver::propagate(lbfgsb200_progress_t *out) {
         if (hit < 0 && cap > 1 && spec_k_ > (int)ls.trials()) {   // (a search that outlives the guess goes on one trial at a time)
             // one pass for this trial and the ones the search is expected to ask for next (as many as the previous search
             // needed): they share the read of xp and d
-            double steps[kSpecMax] = {stp, 0.0, 0.0, 0.0};
+            double steps[kSpecMax] = {};
+            steps[0] = stp;
             int want = spec_k_ - ((int)ls.trials() - 1);     // trials() counts the one just handed out
             if (want > cap) want = cap;
             const int k = 1 + ls.predict(steps + 1, want - 1);

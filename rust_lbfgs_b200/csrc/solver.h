@@ -93,10 +93,10 @@ class Solver {
     struct Speculation;
     // scalar slots in device memory (kMaxAcc doubles each)
     // SLOT_STEP[0]: the next search's first step as formed on the device (speculative first trial)
-    // SLOT_SPEC .. SLOT_SPEC + 2: the results of a multi-step probe, kSpecMax x {f, g.d, g.g, x.x} then the steps used
-    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_STEP = 5, SLOT_SPEC = 6, SLOT_COUNT = 9 };
-    static constexpr int kSpecMax = 4;          // trial points per multi-step probe (5 * kSpecMax doubles <= 3 slots)
-    static constexpr int kHostWords = 128;      // pinned mirror: every slot (72 doubles) + the evaluate-flag staging word
+    // SLOT_SPEC .. SLOT_SPEC + 3: the results of a multi-step probe, kSpecMax x {f, g.d, g.g, x.x} then the steps used
+    enum Slot { SLOT_EVAL = 0, SLOT_HIST = 1, SLOT_LOOP_A = 2, SLOT_LOOP_B = 3, SLOT_INIT = 4, SLOT_STEP = 5, SLOT_SPEC = 6, SLOT_COUNT = 10 };
+    static constexpr int kSpecMax = 6;          // trial points per multi-step probe (5 * kSpecMax doubles <= 4 slots)
+    static constexpr int kHostWords = 128;      // pinned mirror: every slot (80 doubles) + the evaluate-flag staging word
     static constexpr int kFlagWord = 120;
     double *slot(int s) const { return scal_dev_ + (size_t)s * kMaxAcc; }
 
@@ -177,9 +177,9 @@ class Solver {
     // asks for exactly that step.
     // With the objective's multi-step probe the trials the search is EXPECTED to take next (More-Thuente's extrapolation
     // chain, LineSearchMachine::predict) ride in the same pass: up to kSpecMax entries.
-    struct Speculation { int count = 0; double step[4] = {0.0, 0.0, 0.0, 0.0}; double h[4][4] = {}; } spec_;
+    struct Speculation { int count = 0; double step[kSpecMax] = {}; double h[kSpecMax][4] = {}; } spec_;
     int spec_k_ = 1;              // trial points to evaluate per pass: what the previous search needed (adaptive)
-    int multi_probe_max_ = 4;     // LBFGSB200_MULTI_PROBE_MAX (1 disables)
+    int multi_probe_max_ = kSpecMax;   // LBFGSB200_MULTI_PROBE_MAX (1 disables)
     bool speculate_ = true;       // LBFGSB200_SPECULATE=0 disables
     bool built_ = false;
     double fx_ = 0.0, xx_ = 0.0, gg_ = 0.0;   // f(x), x.x, g.g (pg.pg for OWL-QN) at the current point

@@ -45,8 +45,8 @@ constexpr int kMaxAcc = 8;             // accumulators per kernel (and doubles p
 // logic needs.  No NCCL call, no extra launch.
 constexpr int kMaxPeers = 8;
 constexpr int kMailRing = 4;
-constexpr int kMailStride = 24;        // doubles per entry (192 B): [0] = seq word, [1..] = values
-constexpr int kMailVals = 18;          // 16 = four line-search trial points x {f, g.d, g.g, x.x} in one exchange, + 2 riders
+constexpr int kMailStride = 32;        // doubles per entry (256 B): [0] = seq word, [1..] = values
+constexpr int kMailVals = 26;          // 24 = six line-search trial points x {f, g.d, g.g, x.x} in one exchange, + 2 riders
 struct PeerCtx {
     int nranks;                    // 0 / 1 = no exchange
     int rank;

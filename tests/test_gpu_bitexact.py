@@ -348,7 +348,7 @@ def test_multi_step_probe_is_transparent(monkeypatch):
     """Several line-search trials per pass (lbfgsb200_probe_multi_fn): the steps More-Thuente is EXPECTED to take next —
     its extrapolation chain stp + 4 (stp - stx), as many as the previous search needed — are evaluated in the same read
     of xp and d, and a result is used only when the search then asks for exactly that step.  Same bits with 1, 2, 3, 4
-    trial points per pass: every line search (the backtracking ones never predict), step-size caps that make the chain
+    trial points per pass (1 ... 6): every line search (the backtracking ones never predict), step-size caps that make the chain
     long or make it miss, reference-order sums; and far fewer passes where the search extrapolates."""
     import torch
 
@@ -367,7 +367,7 @@ def test_multi_step_probe_is_transparent(monkeypatch):
         for n in (100, 5000, 300_000):
             x0 = perturbed_x0(n, seed=5)
             ref = run(1, builder, x0)
-            for kmax in (2, 3, 4):
+            for kmax in (2, 3, 4, 6):
                 _same_traces(run(kmax, builder, x0), ref, f"{name} n={n} kmax={kmax}")
     # fewer passes over xp and d for the same evaluations (at n = 1e8 every search takes s, 5 s, 21 s[, 85 s]: 3.35 -> 1 per iteration)
     passes = {}
