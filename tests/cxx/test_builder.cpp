@@ -87,6 +87,14 @@ int main(int argc, char **argv) {
     Report r4 = lbfgs().with_max_iterations(5).with_orthantwise(1.0, 0, 99).minimize(x, rosen, default_progress());
     CHECK(r4.status == LBFGSB200_OK_MAX_ITERATIONS && r4.niter == 5);
 
+    // ---- the opt-in compact search direction: same problem, same counts, same answer --------------------------
+    for (int i = 0; i < N; i += 2) { x[i] = -1.2; x[i + 1] = 1.0; }
+    int ncc = 0;
+    Report rc = lbfgs().with_direction(LBFGSB200_DIRECTION_COMPACT).minimize(x, rosen, [&](const Progress &) { ++ncc; return false; });
+    CHECK(rc.status == LBFGSB200_OK_CONVERGED && ncc == 35 && rc.neval == 40);
+    for (double v : x) CHECK(std::fabs(v - 1.0) <= 1e-4);
+    CHECK(panics([&] { std::vector<double> xs(4, 0.5); lbfgs().with_m(33).with_direction(LBFGSB200_DIRECTION_COMPACT).minimize(xs, rosen); }));   // m <= 32
+
     // ---- device-resident x + the iterative API (src/lbfgs.rs:443-566, src/line.rs:9-32) ------------------
     void *xd = nullptr;
     CHECK(lbfgsb200_device_alloc(0, N * sizeof(double), &xd) == 0);
