@@ -355,6 +355,7 @@ class Lbfgs:
             cbp = C.cast(cb, C.c_void_p)
         rep = _lib.Report()
         if self._direction is not None:   # the solver is created inside the call: it takes the process default
+            _require(self._direction != _lib.DIRECTION_COMPACT or self.param.m <= 32, "the compact direction supports m <= 32")
             L.lbfgsb200_set_default_direction(self._direction)
         try:
             st = L.lbfgsb200_minimize_host_ex(C.byref(self.param), ptr, n, n_global, goff, device, comm, ev.fn, ev.user,

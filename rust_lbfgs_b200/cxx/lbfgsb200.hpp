@@ -226,6 +226,7 @@ class Lbfgs {
     // one GPU, copied back.
     Report minimize(std::vector<double> &x, const Objective &objective, ProgressFn progress = nullptr) const {
         lbfgsb200_report_t rep{};
+        const DefaultDirection dd(*this);
         lbfgsb200_objective_set_reduction(objective.handle(), (int)p_.reduction);
         if (comm_) objective.shard(comm_);
         const lbfgsb200_fused_ops_t ops = objective.fused_ops(fused_);
@@ -239,6 +240,7 @@ class Lbfgs {
     }
     Report minimize(std::vector<double> &x, DeviceEvaluate evaluate, ProgressFn progress = nullptr) const {
         lbfgsb200_report_t rep{};
+        const DefaultDirection dd(*this);
         int st = lbfgsb200_minimize_host(&p_, x.data(), (int64_t)x.size(), device_, tramp_eval, &evaluate,
                                          progress ? tramp_progress : nullptr, progress ? &progress : nullptr, &rep);
         Report r = convert(rep, st);
@@ -253,6 +255,18 @@ class Lbfgs {
 
   private:
     friend class LbfgsState;
+    // The host-buffer entry points create their solver themselves: it takes the process-wide default direction.
+    struct DefaultDirection {
+        bool set = false;
+        explicit DefaultDirection(const Lbfgs &b) {
+            if (b.direction_ < 0) return;
+            require(b.direction_ != LBFGSB200_DIRECTION_COMPACT || b.p_.m <= 32, "the compact direction supports m <= 32");
+            set = lbfgsb200_set_default_direction(b.direction_) == 0;
+        }
+        DefaultDirection(const DefaultDirection &) = delete;
+        DefaultDirection &operator=(const DefaultDirection &) = delete;
+        ~DefaultDirection() { if (set) lbfgsb200_set_default_direction(-1); }
+    };
     struct Handle {
         lbfgsb200_solver_t *s = nullptr;
         Handle(const Lbfgs &b, int64_t n) {
@@ -326,6 +340,7 @@ class LbfgsState {
         o.last_ls_error = r.last_ls_error; o.status = (int)r.status; return o;
     }
     void finish() { int st = lbfgsb200_finish(h_.s); if (st != 0) throw Error(st, lbfgsb200_last_error(h_.s)); }
+    int direction() const { return lbfgsb200_get_direction(h_.s); }                          // LBFGSB200_DIRECTION_*
 
   private:
     Lbfgs::Handle h_;

@@ -253,7 +253,10 @@ impl Lbfgs {
         let ops = if self.fused_trial { eval_fn.fused_ops() } else { None };
         let mut rep = sys::lbfgsb200_report_t::default();
         // the solver is created inside the call: it takes the process-wide default
-        if let Some(on) = self.compact { unsafe { sys::lbfgsb200_set_default_direction(on as c_int); } }
+        if let Some(on) = self.compact {
+            assert!(!on || self.param.m <= 32, "the compact direction supports m <= 32");
+            unsafe { sys::lbfgsb200_set_default_direction(on as c_int); }
+        }
         let st = unsafe { sys::lbfgsb200_minimize_host_ex(&self.param, x.as_mut_ptr(), x.len() as i64, n_global, goff, device, comm,
                                                           eval.0, eval.1, ops.as_ref().map_or(std::ptr::null(), |o| o as *const _),
                                                           Some(progress_tramp::<G>), &mut prgr_fn as *mut G as *mut c_void, &mut rep) };

@@ -109,6 +109,19 @@ int main(int argc, char **argv) {
     }
     CHECK(lbfgsb200_copy_d2h(x.data(), xd, N * sizeof(double), nullptr) == 0);
     for (double v : x) CHECK(std::fabs(v - 1.0) <= 1e-4);
+    // the same through the compact direction (the state knows which one it runs)
+    for (int i = 0; i < N; i += 2) { x[i] = -1.2; x[i + 1] = 1.0; }
+    CHECK(lbfgsb200_copy_h2d(xd, x.data(), N * sizeof(double), nullptr) == 0);
+    {
+        LbfgsState st = lbfgs().with_direction(LBFGSB200_DIRECTION_COMPACT).build((double *)xd, N, rosen);
+        CHECK(st.direction() == LBFGSB200_DIRECTION_COMPACT);
+        int k = 0;
+        while (!st.is_converged()) { st.propagate(); ++k; }
+        st.finish();
+        CHECK(k == 35 && st.report().neval == 40);
+    }
+    CHECK(lbfgsb200_copy_d2h(x.data(), xd, N * sizeof(double), nullptr) == 0);
+    for (double v : x) CHECK(std::fabs(v - 1.0) <= 1e-4);
     // cancel from the progress callback (src/lbfgs.rs:412-416)
     CHECK(lbfgsb200_copy_h2d(xd, std::vector<double>(N, 0.5).data(), N * sizeof(double), nullptr) == 0);
     Report r5 = lbfgs().minimize((double *)xd, N, rosen, [](const Progress &p) { return p.niter == 3; });
