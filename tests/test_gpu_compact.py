@@ -273,3 +273,27 @@ def test_compact_small_cluster_kernel_matches_the_three_launch_form(n, monkeypat
             assert s["ncall"] == t["ncall"], (name, s["niter"])
             assert np.max(np.abs(s["x"] - t["x"])) <= 1e-11 * max(1.0, np.max(np.abs(t["x"]))), (name, s["niter"])
     monkeypatch.delenv("LBFGSB200_SMALL")
+
+
+def test_compact_through_the_host_buffer_entry_and_no_leak_of_the_default():
+    """`minimize_host` creates its solver inside the C call: the builder hands the direction over as the process-wide
+    default for the duration of the call.  Same bits as the device-resident call; solvers created afterwards are back
+    on the two-loop recursion."""
+    import torch
+    x0 = perturbed_x0(5000)
+    xh = x0.copy()
+    rep_h = R.lbfgs().with_direction("compact").with_max_iterations(30).minimize_host(xh, R.Rosenbrock())
+    xd = torch.tensor(x0, device="cuda:0")
+    rep_d = R.lbfgs().with_direction("compact").with_max_iterations(30).minimize(xd, R.Rosenbrock())
+    assert rep_h.neval == rep_d.neval and rep_h.fx == rep_d.fx and np.array_equal(xh, xd.cpu().numpy())
+    xt = torch.tensor(x0, device="cuda:0")
+    rep_t = R.lbfgs().with_max_iterations(30).minimize(xt, R.Rosenbrock())
+    assert rep_t.neval == rep_d.neval and not np.array_equal(xt.cpu().numpy(), xh)     # the two-loop path: other rounding
+    st = R.lbfgs().build(torch.tensor(x0, device="cuda:0"), R.Rosenbrock())
+    assert R.lib().lbfgsb200_get_direction(st._solver) == 0
+    st.close()
+    st = R.lbfgs().with_direction("compact").build(torch.tensor(x0, device="cuda:0"), R.Rosenbrock())
+    assert R.lib().lbfgsb200_get_direction(st._solver) == 1
+    st.close()
+    with pytest.raises(ValueError):
+        R.lbfgs().with_m(40).with_direction("compact").minimize_host(x0.copy(), R.Rosenbrock())
