@@ -192,6 +192,14 @@ def cfg4(full):
                                   ms_per_evaluation=ms, ordered_pairs_per_s=na * (na - 1) / (ms / 1e3),
                                   parity="UNPINNED (no reference test for examples/lj.rs; oracle restatement only)")), flush=True)
         lj.close()
+    # (a short solve first: the process's first solver pays for the memory pool, pinned scalars, module loading — the
+    # 0.7 ms per iteration by which the first configuration below exceeded the others in profiles/r02k_configs_8gpu_full.log)
+    bw, ljw = R.lbfgs().with_damping(True).with_max_iterations(3), R.LennardJones()
+    if COMM is not None:
+        ljw.shard(COMM, offs)
+        bw = bw.with_shard(COMM, flat.size, offs[RANK])
+    bw.minimize(x0.clone(), ljw, None)
+    ljw.close()
     for tag, mk in (("gradient-only max_linesearch=2", lambda: R.lbfgs().with_gradient_only().with_max_linesearch(2)),
                     ("damped", lambda: R.lbfgs().with_damping(True))):
         for fast in (False, True):
