@@ -237,3 +237,40 @@ def test_predictions_are_the_extrapolation_chain_and_change_nothing(oracle):
     finally:
         PREDICT_STATS = None
     assert stats["made"] > 200 and stats["hit"] > 0.5 * stats["made"], stats
+
+
+def test_predict_is_silent_where_nothing_is_predictable():
+    """No prediction before a trial was handed out, after the search ended, for the backtracking searches (their next
+    step depends on which test failed), for OWL-QN, or once More-Thuente has bracketed the minimum."""
+    L = R.lib()
+    buf = (C.c_double * 4)()
+    stp = C.c_double()
+    for algo, owl in ((1, 0), (2, 0), (3, 0), (1, 1)):
+        pp = R.default_param()
+        pp.ls_algorithm = algo
+        h = L.lbfgsb200_linesearch_begin(C.byref(pp), owl, 1.0, -1.0, 0.5)
+        assert L.lbfgsb200_linesearch_predict(h, buf, 4) == 0
+        assert L.lbfgsb200_linesearch_next(h, C.byref(stp))
+        assert L.lbfgsb200_linesearch_predict(h, buf, 4) == 0
+        L.lbfgsb200_linesearch_end(h)
+    pp = R.default_param()
+    h = L.lbfgsb200_linesearch_begin(C.byref(pp), 0, 0.0, -1.0, 0.05)      # phi(t) = (t - 3)^2 / 6 - 1.5: minimum at 3
+    assert L.lbfgsb200_linesearch_predict(h, buf, 4) == 0                  # nothing handed out yet
+    seen = []
+    while L.lbfgsb200_linesearch_next(h, C.byref(stp)):
+        t = stp.value
+        n_pred = L.lbfgsb200_linesearch_predict(h, buf, 4)
+        seen.append((t, n_pred))
+        L.lbfgsb200_linesearch_feed(h, 1, (t - 3.0) ** 2 / 6.0 - 1.5, (t - 3.0) / 3.0)
+    assert L.lbfgsb200_linesearch_predict(h, buf, 4) == 0                  # search over
+    ncall = C.c_int64()
+    assert L.lbfgsb200_linesearch_result(h, C.byref(ncall), None) == 0
+    L.lbfgsb200_linesearch_end(h)
+    assert seen[0][1] > 0                                                  # first trial: still extrapolating
+    assert len(seen) >= 2 and ncall.value == len(seen)
+    # max_linesearch bounds the chain: with 3 trials allowed at most 1 further step is predicted after the first
+    pp.ls_max_linesearch = 3
+    h = L.lbfgsb200_linesearch_begin(C.byref(pp), 0, 0.0, -1.0, 1e-3)
+    assert L.lbfgsb200_linesearch_next(h, C.byref(stp))
+    assert L.lbfgsb200_linesearch_predict(h, buf, 4) == 1
+    L.lbfgsb200_linesearch_end(h)
