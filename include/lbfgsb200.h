@@ -509,6 +509,10 @@ int  lbfgsb200_stream_synchronize(void *stream);
  * n-vectors each time.  This hands the cached pages back to the driver (e.g. before another library needs the
  * HBM).  LBFGSB200_POOL=0 disables the pool. */
 int  lbfgsb200_trim_pool(int device);
+/* 3.  Everything added since ABI 3 was first published is additive: new functions (lbfgsb200_set_direction,
+ * _get_direction, _set_default_direction, _linesearch_predict, _objective_probe_multi, _objective_commit_gram) and two
+ * optional entries appended to lbfgsb200_fused_ops_t, whose struct_size tells the library which layout the caller
+ * was built against (LBFGSB200_FUSED_OPS_SIZE_V1 / _V2 / sizeof). */
 int  lbfgsb200_abi_version(void);
 
 #ifdef __cplusplus
